@@ -1,0 +1,731 @@
+// K7 -- LSMR (Fong & Saunders) with local reorthogonalisation on one B200, replacing
+// LSMRmodule::LSMR (src/lsmrModule.f90:36-750), aprod (src/aprod.f90:7-60) and the REAL*4
+// dnrm2/dscal of src/lsmrblas.f90:247-359.
+//
+// Data layout in HBM: the COO triplets the reference passes in iw/rw are turned once per call
+// into CSR (for u += A v) and CSC (for v += A' u) so that both products stream (col,val) /
+// (row,val) pairs with fully coalesced 128-byte warp loads and gather the (L2-resident) dense
+// vector.  Storage is fp32 like the reference (real(dp) is REAL*4, lsmrDataModule.f90:21);
+// every reduction (row sums, norms, dot products) accumulates in fp64 in a fixed order, so the
+// result is deterministic and at least as accurate as the reference's serial fp32 sums.
+// Scalar recurrences (plane rotations, norm/cond estimates, stopping rules) are evaluated in
+// fp32 in the reference's operation order by single-thread kernels, so no host round trip is
+// needed inside an iteration except reading the stop flag.
+//
+// Bound: HBM bandwidth.  Algorithmic bytes per iteration:
+//   16*nnz + 8*(m+1) + 12*m + 80*n.
+#include <cub/cub.cuh>
+#include <vector>
+#include "../../include/dsurftomo_b200.h"
+#include "common.cuh"
+#include "lsmr.cuh"
+
+namespace dsurf {
+
+// ---------------------------------------------------------------------------------------------
+// sparse products: one warp per row of the compressed structure (CSR row or CSC column)
+//   y[r] = float( double(fl(s * y[r])) + sum_k double(val[k]) * double(x[idx[k]]) )
+// (the reference first scales y by s with dscal, then accumulates, lsmrModule.f90:484-486,495-497)
+// Optionally accumulates sum(y^2) per block into partial[blockIdx.x] (fixed order).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSpmvWarps = 8;
+
+__global__ void __launch_bounds__(kSpmvWarps * 32)
+k_spmv_warp(const long long *__restrict__ ptr, const int *__restrict__ idx,
+            const float *__restrict__ val, const float *__restrict__ x, float *__restrict__ y,
+            const float *__restrict__ scale_ptr, float scale_sign, int nrows,
+            double *__restrict__ partial, const int *__restrict__ stop) {
+  __shared__ double sh[kSpmvWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.x * kSpmvWarps + w;
+  double sq = 0.0;
+  if (stop == nullptr || *stop == 0) {
+    if (r < nrows) {
+      const long long b = ptr[r], e = ptr[r + 1];
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+      long long k = b + lane;
+      for (; k + 96 < e; k += 128) {  // 4 independent 128-byte streams in flight per array
+        const int i0 = idx[k], i1 = idx[k + 32], i2 = idx[k + 64], i3 = idx[k + 96];
+        const float v0 = val[k], v1 = val[k + 32], v2 = val[k + 64], v3 = val[k + 96];
+        acc0 += (double)v0 * (double)__ldg(x + i0);
+        acc1 += (double)v1 * (double)__ldg(x + i1);
+        acc2 += (double)v2 * (double)__ldg(x + i2);
+        acc3 += (double)v3 * (double)__ldg(x + i3);
+      }
+      for (; k < e; k += 32) acc0 += (double)val[k] * (double)__ldg(x + idx[k]);
+      double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
+      if (lane == 0) {
+        const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
+        const float y0 = scale_ptr ? s * y[r] : 0.0f;
+        const float yn = (float)((double)y0 + acc);
+        y[r] = yn;
+        sq = (double)yn * (double)yn;
+      }
+    }
+  }
+  if (partial) {
+    if (lane == 0) sh[w] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < kSpmvWarps; i++) t += sh[i];
+      partial[blockIdx.x] = t;
+    }
+  }
+}
+
+// one-block deterministic reduction of `np` partials (fixed strided order + tree)
+__device__ double block_reduce_partials(const double *partial, int np) {
+  __shared__ double sh[1024];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) t += partial[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  return sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar state (all REAL*4 like the reference's locals, lsmrModule.f90:336-351)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float d2norm_f(float a, float b) {  // lsmrModule.f90:686-709
+  const float scale = fabsf(a) + fabsf(b);
+  if (scale == 0.0f) return 0.0f;
+  const float ra = a / scale, rb = b / scale;
+  return scale * sqrtf(ra * ra + rb * rb);
+}
+
+// after u = A v - alpha u : beta = ||u||  (plus its all-reduced partner in multi-GPU runs)
+__global__ void k_beta(LsmrScalars *S, const double *partial, int np, const double *extra) {
+  if (S->stop) return;
+  double s = block_reduce_partials(partial, np);
+  if (threadIdx.x == 0) {
+    if (extra) s = *extra;  // multi-GPU: globally reduced sum of squares
+    S->sum_u2 = s;
+    const float beta = (float)sqrt(s);
+    S->beta = beta;
+    S->beta_pos = beta > 0.0f;
+    S->inv_beta = beta > 0.0f ? 1.0f / beta : 0.0f;
+    S->neg_beta = -beta;
+  }
+}
+
+// u *= 1/beta (m) ; localV enqueue (lsmrModule.f90:715-726) ; v *= -beta is folded into the
+// spmtv kernel's scale argument.
+__global__ void k_scale_u_enqueue(const LsmrScalars *S, float *u, int m, const float *v,
+                                  float *localV, int n, int do_enqueue) {
+  if (S->stop || !S->beta_pos) return;
+  const float ib = S->inv_beta;
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += tot) u[i] = ib * u[i];
+  if (do_enqueue) {
+    float *q = localV + (size_t)S->enq_slot * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) q[i] = v[i];
+  }
+}
+
+// advance the circular-buffer pointer (lsmrModule.f90:717-724) -- before k_scale_u_enqueue
+__global__ void k_enqueue_ptr(LsmrScalars *S, int localVecs) {
+  if (S->stop || !S->beta_pos) return;
+  if (S->localPointer < localVecs) {
+    S->localPointer = S->localPointer + 1;
+  } else {
+    S->localPointer = 1;
+    S->queueFull = 1;
+  }
+  S->enq_slot = S->localPointer - 1;
+  S->orthoLimit = S->queueFull ? localVecs : S->localPointer;
+}
+
+// reorthogonalisation step c (lsmrModule.f90:741-746):  v -= d_{c-1} q_{c-1} (if c>0), then
+// partial dot(v, q_c) (if c < limit) or partial sum(v^2) (if c == limit).
+__global__ void k_reorth(const LsmrScalars *S, float *v, const float *localV, int n, int c,
+                         double *partial) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  if (!S->stop && S->beta_pos) {
+    const int lim = S->orthoLimit;
+    if (c <= lim) {
+      const float dprev = S->dot_d;
+      const float *qp = (c > 0) ? localV + (size_t)(c - 1) * n : nullptr;
+      const float *qc = (c < lim) ? localV + (size_t)c * n : nullptr;
+      const long long tot = (long long)gridDim.x * blockDim.x;
+      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) {
+        float vi = v[i];
+        if (qp) {
+          vi = vi - dprev * qp[i];
+          v[i] = vi;
+        }
+        acc += qc ? (double)vi * (double)qc[i] : (double)vi * (double)vi;
+      }
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// finish step c: d_c = dot (REAL*4), or alpha = ||v|| when c == limit
+__global__ void k_reorth_fin(LsmrScalars *S, const double *partial, int np, int c) {
+  if (S->stop || !S->beta_pos) return;
+  if (c > S->orthoLimit) return;
+  const double s = block_reduce_partials(partial, np);
+  if (threadIdx.x == 0) {
+    if (c < S->orthoLimit) {
+      S->dot_d = (float)s;
+    } else {
+      const float alpha = (float)sqrt(s);
+      S->alpha = alpha;
+      S->inv_alpha = alpha > 0.0f ? 1.0f / alpha : 1.0f;
+      S->alpha_pos = alpha > 0.0f;
+    }
+  }
+}
+
+// plane rotations + estimates up to the vector updates (lsmrModule.f90:508-537)
+__global__ void k_rotations(LsmrScalars *S, float damp) {
+  if (S->stop) return;
+  const float alpha = S->alpha, beta = S->beta;
+  const float alphahat = d2norm_f(S->alphabar, damp);
+  const float chat = S->alphabar / alphahat;
+  const float shat = damp / alphahat;
+  const float rhoold = S->rho;
+  const float rho = d2norm_f(alphahat, beta);
+  const float c = alphahat / rho;
+  const float s = beta / rho;
+  const float thetanew = s * alpha;
+  S->alphabar = c * alpha;
+  const float rhobarold = S->rhobar;
+  const float zetaold = S->zeta;
+  const float thetabar = S->sbar * rho;
+  const float rhotemp = S->cbar * rho;
+  const float rhobar = d2norm_f(S->cbar * rho, thetanew);
+  const float cbar = S->cbar * rho / rhobar;
+  const float sbar = thetanew / rhobar;
+  const float zeta = cbar * S->zetabar;
+  const float zetabar = -sbar * S->zetabar;
+  S->rho = rho;
+  S->rhobar = rhobar;
+  S->cbar = cbar;
+  S->sbar = sbar;
+  S->zeta = zeta;
+  S->zetabar = zetabar;
+  S->f1 = thetabar * rho / (rhoold * rhobarold);
+  S->f2 = zeta / (rho * rhobar);
+  S->f3 = thetanew / rho;
+  // ||r|| estimate (lsmrModule.f90:546-572)
+  const float betaacute = chat * S->betadd;
+  const float betacheck = -shat * S->betadd;
+  const float betahat = c * betaacute;
+  S->betadd = -s * betaacute;
+  const float thetatildeold = S->thetatilde;
+  const float rhotildeold = d2norm_f(S->rhodold, thetabar);
+  const float ctildeold = S->rhodold / rhotildeold;
+  const float stildeold = thetabar / rhotildeold;
+  S->thetatilde = stildeold * rhobar;
+  S->rhodold = ctildeold * rhobar;
+  S->betad = -stildeold * S->betad + ctildeold * betahat;
+  S->tautildeold = (zetaold - thetatildeold * S->tautildeold) / rhotildeold;
+  const float taud = (zeta - S->thetatilde * S->tautildeold) / S->rhodold;
+  S->d = S->d + betacheck * betacheck;
+  {
+    const float e = S->betad - taud;
+    S->normr = sqrtf(S->d + e * e + S->betadd * S->betadd);
+  }
+  // ||A||, cond(A) (lsmrModule.f90:574-584)
+  S->normA2 = S->normA2 + beta * beta;
+  S->normA = sqrtf(S->normA2);
+  S->normA2 = S->normA2 + alpha * alpha;
+  S->maxrbar = fmaxf(S->maxrbar, rhobarold);
+  if (S->itn + 1 > 1) S->minrbar = fminf(S->minrbar, rhobarold);
+  S->condA = fmaxf(S->maxrbar, rhotemp) / fminf(S->minrbar, rhotemp);
+  S->normAr = fabsf(zetabar);
+}
+
+// v *= 1/alpha ; hbar = h - f1 hbar ; x = x + f2 hbar ; h = v - f3 h ; partial sum(x^2)
+// (lsmrModule.f90:503-505, 539-541)
+__global__ void k_update(const LsmrScalars *S, float *v, float *h, float *hbar, float *x, int n,
+                         double *partial) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  if (!S->stop) {
+    const bool scale_v = S->beta_pos && S->alpha_pos;
+    const float ia = S->inv_alpha, f1 = S->f1, f2 = S->f2, f3 = S->f3;
+    const long long tot = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) {
+      float vi = v[i];
+      if (scale_v) {
+        vi = ia * vi;
+        v[i] = vi;
+      }
+      const float hb = h[i] - f1 * hbar[i];
+      hbar[i] = hb;
+      const float xi = x[i] + f2 * hb;
+      x[i] = xi;
+      h[i] = vi - f3 * h[i];
+      acc += (double)xi * (double)xi;
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// normx + stopping rules (lsmrModule.f90:586-616)
+__global__ void k_tests(LsmrScalars *S, const double *partial, int np, float atol, float btol,
+                        float ctol, int itnlim, int force_iters) {
+  if (S->stop) return;
+  const double s = block_reduce_partials(partial, np);
+  if (threadIdx.x != 0) return;
+  const float one = 1.0f;
+  S->itn = S->itn + 1;
+  const float normx = (float)sqrt(s);
+  S->normx = normx;
+  const float test1 = S->normr / S->normb;
+  const float test2 = S->normAr / (S->normA * S->normr);
+  const float test3 = one / S->condA;
+  const float t1 = test1 / (one + S->normA * normx / S->normb);
+  const float rtol = btol + atol * S->normA * normx / S->normb;
+  int istop = 0;
+  if (S->itn >= itnlim) istop = 7;
+  if (!force_iters) {
+    if (one + test3 <= one) istop = 6;
+    if (one + test2 <= one) istop = 5;
+    if (one + t1 <= one) istop = 4;
+    if (test3 <= ctol) istop = 3;
+    if (test2 <= atol) istop = 2;
+    if (test1 <= rtol) istop = 1;
+  }
+  S->istop = istop;
+  if (istop != 0) S->stop = 1;
+}
+
+// initial phase: after u=b, beta=||u||: scale; after v=A'u: alpha, scale, h=v, localV(:,1)=v
+__global__ void k_init_scale_copy(float *dst, const float *src, float *dst2, const float *scale,
+                                  long long n) {
+  const float s = *scale;
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) {
+    const float t = s * src[i];
+    dst[i] = t;
+    if (dst2) dst2[i] = t;
+  }
+}
+__global__ void k_sumsq(const float *x, long long n, double *partial) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot)
+    acc += (double)x[i] * (double)x[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void k_init_beta(LsmrScalars *S, const double *partial, int np, const double *extra) {
+  double s = block_reduce_partials(partial, np);
+  if (threadIdx.x == 0) {
+    if (extra) s = *extra;
+    const float beta = (float)sqrt(s);
+    S->beta = beta;
+    S->inv_beta = beta > 0.0f ? 1.0f / beta : 0.0f;
+    S->beta_pos = beta > 0.0f;
+  }
+}
+__global__ void k_init_alpha(LsmrScalars *S, const double *partial, int np, int localVecs) {
+  const double s = block_reduce_partials(partial, np);
+  if (threadIdx.x == 0) {
+    const float alpha = S->beta_pos ? (float)sqrt(s) : 0.0f;
+    const float beta = S->beta;
+    S->alpha = alpha;
+    S->inv_alpha = alpha > 0.0f ? 1.0f / alpha : 1.0f;
+    S->alpha_pos = alpha > 0.0f;
+    S->normAr = alpha * beta;
+    S->itn = 0;
+    S->zetabar = alpha * beta;
+    S->alphabar = alpha;
+    S->rho = 1;
+    S->rhobar = 1;
+    S->cbar = 1;
+    S->sbar = 0;
+    S->betadd = beta;
+    S->betad = 0;
+    S->rhodold = 1;
+    S->tautildeold = 0;
+    S->thetatilde = 0;
+    S->zeta = 0;
+    S->d = 0;
+    S->normA2 = alpha * alpha;
+    S->maxrbar = 0.0f;
+    S->minrbar = 1e+30f;
+    S->normb = beta;
+    S->istop = 0;
+    S->normr = beta;
+    S->localPointer = 1;
+    S->queueFull = 0;
+    S->enq_slot = 0;
+    S->orthoLimit = localVecs > 0 ? 1 : 0;
+    S->dot_d = 0.0f;
+    S->stop = (alpha * beta == 0.0f) ? 1 : 0;  // lsmrModule.f90:399-400: exit if A'b = 0
+    S->normA = 0;
+    S->condA = 0;
+    S->normx = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// COO -> CSR / CSC
+// ---------------------------------------------------------------------------------------------
+__global__ void k_count(const int *keys1, long long nnz, int *cnt) {
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz; i += tot)
+    atomicAdd(cnt + (keys1[i] - 1), 1);
+}
+__global__ void k_check_sorted(const int *keys1, long long nnz, int *flag) {
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i + 1 < nnz; i += tot)
+    if (keys1[i] > keys1[i + 1]) *flag = 1;
+}
+__global__ void k_iota(int *a, long long n) {
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) a[i] = (int)i;
+}
+__global__ void k_gather_pairs(const int *perm, const int *other1, const float *vals, long long nnz,
+                               int *out_idx0, float *out_val) {
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz; i += tot) {
+    const int p = perm[i];
+    out_idx0[i] = other1[p] - 1;
+    out_val[i] = vals[p];
+  }
+}
+__global__ void k_to_ptr(const int *cnt, const long long *scan_excl, int nrows, long long nnz,
+                         long long *ptr) {
+  const int tot = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= nrows; i += tot)
+    ptr[i] = (i < nrows) ? scan_excl[i] : nnz;
+}
+__global__ void k_widen(const int *cnt, long long *out, int n) {
+  const int tot = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += tot) out[i] = cnt[i];
+}
+
+static int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Builds ptr/idx/val compressed by `keys1` (1-based, nkeys distinct) from COO; stable in k.
+static int build_compressed(cudaStream_t st, const int *keys1, const int *other1, const float *vals,
+                            long long nnz, int nkeys, DevBuf<long long> &ptr, DevBuf<int> &idx,
+                            DevBuf<float> &val) {
+  DevBuf<int> cnt, flag;
+  DevBuf<long long> wide, scan;
+  if (cnt.reserve(nkeys + 1) || flag.reserve(1) || wide.reserve(nkeys + 1) || scan.reserve(nkeys + 1) ||
+      ptr.reserve(nkeys + 1) || idx.reserve(nnz > 0 ? nnz : 1) || val.reserve(nnz > 0 ? nnz : 1)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed in build_compressed");
+    return DSURF_ERR_CUDA;
+  }
+  DS_CUDA(cudaMemsetAsync(cnt.p, 0, (nkeys + 1) * sizeof(int), st));
+  DS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+  if (nnz > 0) {
+    k_count<<<grid_for(nnz), 256, 0, st>>>(keys1, nnz, cnt.p);
+    k_check_sorted<<<grid_for(nnz), 256, 0, st>>>(keys1, nnz, flag.p);
+  }
+  k_widen<<<grid_for(nkeys + 1), 256, 0, st>>>(cnt.p, wide.p, nkeys + 1);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, wide.p, scan.p, nkeys + 1, st);
+  DevBuf<char> tmp;
+  if (tmp.reserve(tb + 16)) return DSURF_ERR_CUDA;
+  cub::DeviceScan::ExclusiveSum(tmp.p, tb, wide.p, scan.p, nkeys + 1, st);
+  k_to_ptr<<<grid_for(nkeys + 1), 256, 0, st>>>(cnt.p, scan.p, nkeys, nnz, ptr.p);
+  int hflag = 0;
+  DS_CUDA(cudaMemcpyAsync(&hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  if (nnz == 0) return DSURF_OK;
+  if (!hflag) {  // already grouped by key in ascending order: identity permutation
+    DevBuf<int> perm;
+    if (perm.reserve(nnz)) return DSURF_ERR_CUDA;
+    k_iota<<<grid_for(nnz), 256, 0, st>>>(perm.p, nnz);
+    k_gather_pairs<<<grid_for(nnz), 256, 0, st>>>(perm.p, other1, vals, nnz, idx.p, val.p);
+    DS_CUDA(cudaStreamSynchronize(st));
+    return DSURF_OK;
+  }
+  // stable radix sort of (key, k) pairs
+  DevBuf<int> k_in, k_out, p_in, p_out;
+  if (k_out.reserve(nnz) || p_in.reserve(nnz) || p_out.reserve(nnz)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (sort buffers)");
+    return DSURF_ERR_CUDA;
+  }
+  k_iota<<<grid_for(nnz), 256, 0, st>>>(p_in.p, nnz);
+  int end_bit = 1;
+  while ((1ll << end_bit) <= (long long)nkeys + 1 && end_bit < 31) end_bit++;
+  size_t sb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sb, keys1, k_out.p, p_in.p, p_out.p, (long long)nnz, 0, end_bit, st);
+  DevBuf<char> stmp;
+  if (stmp.reserve(sb + 16)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (sort temp)");
+    return DSURF_ERR_CUDA;
+  }
+  cub::DeviceRadixSort::SortPairs(stmp.p, sb, keys1, k_out.p, p_in.p, p_out.p, (long long)nnz, 0, end_bit, st);
+  k_gather_pairs<<<grid_for(nnz), 256, 0, st>>>(p_out.p, other1, vals, nnz, idx.p, val.p);
+  DS_CUDA(cudaStreamSynchronize(st));
+  DS_CUDA(cudaGetLastError());
+  return DSURF_OK;
+}
+
+}  // namespace dsurf
+
+using namespace dsurf;
+
+struct dsurf_lsmr_sys {
+  int m = 0, n = 0;
+  long long nnz = 0;
+  cudaStream_t st = nullptr;
+  DevBuf<long long> row_ptr, col_ptr;
+  DevBuf<int> csr_col, csc_row;
+  DevBuf<float> csr_val, csc_val;
+  DevBuf<float> b, u, v, h, hbar, x, localV;
+  DevBuf<double> partial;
+  DevBuf<LsmrScalars> S;
+  int np_cap = 0;
+  // multi-GPU (rows partitioned over ranks): see lsmr_dist in capi.cu
+  void *comm = nullptr;
+  int rank = 0, nranks = 1;
+  DevBuf<float> vpart;
+  DevBuf<double> red;
+};
+
+namespace dsurf {
+int lsmr_allreduce(void *comm, float *buf, size_t n, double *dbuf, size_t nd, cudaStream_t st);  // capi.cu
+
+int lsmr_sys_create_dev(dsurf_lsmr_sys **out, int m, int n, long long nnz, const int *d_rows1,
+                        const int *d_cols1, const float *d_vals, const float *d_b, cudaStream_t st) {
+  auto *s = new dsurf_lsmr_sys();
+  s->m = m;
+  s->n = n;
+  s->nnz = nnz;
+  s->st = st;
+  int rc = build_compressed(st, d_rows1, d_cols1, d_vals, nnz, m, s->row_ptr, s->csr_col, s->csr_val);
+  if (rc == DSURF_OK) rc = build_compressed(st, d_cols1, d_rows1, d_vals, nnz, n, s->col_ptr, s->csc_row, s->csc_val);
+  if (rc != DSURF_OK) {
+    delete s;
+    return rc;
+  }
+  const int np = std::max((m + kSpmvWarps - 1) / kSpmvWarps, (n + kSpmvWarps - 1) / kSpmvWarps) + 1024;
+  s->np_cap = np;
+  if (s->b.reserve(m) || s->u.reserve(m) || s->v.reserve(n) || s->h.reserve(n) || s->hbar.reserve(n) ||
+      s->x.reserve(n) || s->partial.reserve(np) || s->S.reserve(1) || s->vpart.reserve(n + 8) ||
+      s->red.reserve(8)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (lsmr vectors)");
+    delete s;
+    return DSURF_ERR_CUDA;
+  }
+  cudaMemcpyAsync(s->b.p, d_b, (size_t)m * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  cudaStreamSynchronize(st);
+  *out = s;
+  return DSURF_OK;
+}
+}  // namespace dsurf
+
+extern "C" int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar, const int *rows1,
+                                 const int *cols1, const float *vals, const float *b) {
+  DS_CHECK(ensure_device());
+  if (!sys || m <= 0 || n <= 0 || nar < 0) return DSURF_ERR_BAD_ARG;
+  DevBuf<int> dr, dc;
+  DevBuf<float> dv, db;
+  const size_t nn = nar > 0 ? (size_t)nar : 1;
+  if (dr.reserve(nn) || dc.reserve(nn) || dv.reserve(nn) || db.reserve(m)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (COO upload)");
+    return DSURF_ERR_CUDA;
+  }
+  DS_CUDA(cudaMemcpy(dr.p, rows1, nar * sizeof(int), cudaMemcpyHostToDevice));
+  DS_CUDA(cudaMemcpy(dc.p, cols1, nar * sizeof(int), cudaMemcpyHostToDevice));
+  DS_CUDA(cudaMemcpy(dv.p, vals, nar * sizeof(float), cudaMemcpyHostToDevice));
+  DS_CUDA(cudaMemcpy(db.p, b, (size_t)m * sizeof(float), cudaMemcpyHostToDevice));
+  return lsmr_sys_create_dev(sys, m, n, nar, dr.p, dc.p, dv.p, db.p, 0);
+}
+
+extern "C" int dsurf_lsmr_destroy(dsurf_lsmr_sys *sys) {
+  delete sys;
+  return DSURF_OK;
+}
+extern "C" int64_t dsurf_lsmr_nnz(const dsurf_lsmr_sys *sys) { return sys ? sys->nnz : 0; }
+extern "C" int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *comm, int rank, int nranks) {
+  if (!sys) return DSURF_ERR_BAD_ARG;
+  sys->comm = comm;
+  sys->rank = rank;
+  sys->nranks = nranks;
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float btol, float conlim,
+                                int itnlim, int localSize, int force_iters, float *x_host, int *istop,
+                                int *itn, float *normA, float *condA, float *normr, float *normAr,
+                                float *normx, double *ms_total, double *ms_spmv, double *ms_spmtv) {
+  if (!s) return DSURF_ERR_BAD_ARG;
+  DS_CHECK(ensure_device());
+  cudaStream_t st = s->st;
+  const int m = s->m, n = s->n;
+  const int localVecs = std::min(localSize, std::min(m, n));
+  if (localVecs > 0 && s->localV.reserve((size_t)n * localVecs)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (localV)");
+    return DSURF_ERR_CUDA;
+  }
+  LsmrScalars *S = s->S.p;
+  double *part = s->partial.p;
+  const int gu = (m + kSpmvWarps - 1) / kSpmvWarps, gv = (n + kSpmvWarps - 1) / kSpmvWarps;
+  const int gvec = std::min(std::max((n + 255) / 256, 1), sm_count() * 4);
+  const int gvecm = std::min(std::max((std::max(m, n) + 255) / 256, 1), sm_count() * 4);
+  const float ctol = conlim > 0.0f ? 1.0f / conlim : 0.0f;
+  cudaEvent_t e0, e1, ea, eb, ec, ed;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&ea); cudaEventCreate(&eb);
+  cudaEventCreate(&ec); cudaEventCreate(&ed);
+  double t_spmv = 0, t_spmtv = 0;
+  DS_CUDA(cudaMemsetAsync(S, 0, sizeof(LsmrScalars), st));
+  DS_CUDA(cudaMemsetAsync(s->x.p, 0, (size_t)n * sizeof(float), st));
+  DS_CUDA(cudaMemsetAsync(s->hbar.p, 0, (size_t)n * sizeof(float), st));
+  DS_CUDA(cudaMemsetAsync(s->v.p, 0, (size_t)n * sizeof(float), st));
+  cudaEventRecord(e0, st);
+  // ---- u = b ; beta = ||u|| ; u /= beta ; v = A'u ; alpha = ||v|| ; v /= alpha (:380-397)
+  k_sumsq<<<gvecm, 256, 0, st>>>(s->b.p, m, part);
+  k_init_beta<<<1, 1024, 0, st>>>(S, part, gvecm, nullptr);
+  k_init_scale_copy<<<gvecm, 256, 0, st>>>(s->u.p, s->b.p, nullptr, &S->inv_beta, m);
+  k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
+                                              nullptr, 0.0f, n, part, nullptr);
+  k_init_alpha<<<1, 1024, 0, st>>>(S, part, gv, localVecs);
+  k_init_scale_copy<<<gvec, 256, 0, st>>>(s->v.p, s->v.p, s->h.p, &S->inv_alpha, n);
+  if (localVecs > 0)
+    DS_CUDA(cudaMemcpyAsync(s->localV.p, s->v.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  int h_stop = 0;
+  DS_CUDA(cudaMemcpyAsync(&h_stop, &S->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  int iters_launched = 0;
+  while (!h_stop) {
+    // u = A v - alpha u ; beta (:484-487)
+    cudaEventRecord(ea, st);
+    k_spmv_warp<<<gu, kSpmvWarps * 32, 0, st>>>(s->row_ptr.p, s->csr_col.p, s->csr_val.p, s->v.p, s->u.p,
+                                                &S->alpha, -1.0f, m, part, &S->stop);
+    cudaEventRecord(eb, st);
+    k_beta<<<1, 1024, 0, st>>>(S, part, gu, nullptr);
+    if (localVecs > 0) k_enqueue_ptr<<<1, 1, 0, st>>>(S, localVecs);
+    k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    // v = A'u - beta v (:495-497)
+    cudaEventRecord(ec, st);
+    k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
+                                                &S->neg_beta, 1.0f, n, nullptr, &S->stop);
+    cudaEventRecord(ed, st);
+    // local reorthogonalisation + alpha (:498-504, 731-748); steps beyond the current limit no-op
+    const int maxsteps = localVecs;  // c = 0..limit, limit <= localVecs
+    for (int c = 0; c <= maxsteps; c++) {
+      k_reorth<<<gvec, 256, 0, st>>>(S, s->v.p, s->localV.p, n, c, part);
+      k_reorth_fin<<<1, 256, 0, st>>>(S, part, gvec, c);
+    }
+    k_rotations<<<1, 1, 0, st>>>(S, damp);
+    k_update<<<gvec, 256, 0, st>>>(S, s->v.p, s->h.p, s->hbar.p, s->x.p, n, part);
+    k_tests<<<1, 1024, 0, st>>>(S, part, gvec, atol, btol, ctol, itnlim, force_iters);
+    DS_CUDA(cudaMemcpyAsync(&h_stop, &S->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    float ms;
+    cudaEventElapsedTime(&ms, ea, eb); t_spmv += ms;
+    cudaEventElapsedTime(&ms, ec, ed); t_spmtv += ms;
+    iters_launched++;
+    if (iters_launched > itnlim + 2) break;
+  }
+  cudaEventRecord(e1, st);
+  LsmrScalars hs;
+  DS_CUDA(cudaMemcpyAsync(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  if (x_host) DS_CUDA(cudaMemcpyAsync(x_host, s->x.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  DS_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_total) *ms_total = ms;
+  if (ms_spmv) *ms_spmv = t_spmv;
+  if (ms_spmtv) *ms_spmtv = t_spmtv;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ea); cudaEventDestroy(eb);
+  cudaEventDestroy(ec); cudaEventDestroy(ed);
+  int is = hs.istop;
+  if (damp > 0.0f && is == 2) is = 3;  // lsmrModule.f90:654
+  if (istop) *istop = is;
+  if (itn) *itn = hs.itn;
+  if (normA) *normA = hs.normA;
+  if (condA) *condA = hs.condA;
+  if (normr) *normr = hs.normr;
+  if (normAr) *normAr = hs.normAr;
+  if (normx) *normx = hs.normx;
+  return DSURF_OK;
+}
+
+// aprod drop-in: one product on the device (mode 1: y += A x, mode 2: x += A'y); the COO is
+// compressed on the fly, so this entry point exists for interface completeness and tests --
+// LSMR itself never calls it.
+extern "C" int dsurf_aprod(int mode, int m, int n, float *x, float *y, int leniw, int lenrw,
+                           const int *iw, const float *rw) {
+  DS_CHECK(ensure_device());
+  if (!iw || !rw || leniw < 1) return DSURF_ERR_BAD_ARG;
+  const long long nar = iw[0];
+  if (leniw < 2 * nar + 1 || lenrw < nar) return DSURF_ERR_BAD_ARG;
+  DevBuf<int> dr, dc;
+  DevBuf<float> dv, dx, dy;
+  DevBuf<long long> ptr;
+  DevBuf<int> idx;
+  DevBuf<float> val;
+  const size_t nn = nar > 0 ? nar : 1;
+  if (dr.reserve(nn) || dc.reserve(nn) || dv.reserve(nn) || dx.reserve(n) || dy.reserve(m)) return DSURF_ERR_CUDA;
+  DS_CUDA(cudaMemcpy(dr.p, iw + 1, nar * sizeof(int), cudaMemcpyHostToDevice));
+  DS_CUDA(cudaMemcpy(dc.p, iw + 1 + nar, nar * sizeof(int), cudaMemcpyHostToDevice));
+  DS_CUDA(cudaMemcpy(dv.p, rw, nar * sizeof(float), cudaMemcpyHostToDevice));
+  DS_CUDA(cudaMemcpy(dx.p, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  DS_CUDA(cudaMemcpy(dy.p, y, (size_t)m * sizeof(float), cudaMemcpyHostToDevice));
+  DevBuf<float> one;
+  if (one.reserve(1)) return DSURF_ERR_CUDA;
+  const float h1 = 1.0f;
+  DS_CUDA(cudaMemcpy(one.p, &h1, sizeof(float), cudaMemcpyHostToDevice));
+  if (mode == 1) {
+    DS_CHECK(build_compressed(0, dr.p, dc.p, dv.p, nar, m, ptr, idx, val));
+    k_spmv_warp<<<(m + kSpmvWarps - 1) / kSpmvWarps, kSpmvWarps * 32>>>(ptr.p, idx.p, val.p, dx.p, dy.p,
+                                                                        one.p, 1.0f, m, nullptr, nullptr);
+    DS_CUDA(cudaMemcpy(y, dy.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost));
+  } else {
+    DS_CHECK(build_compressed(0, dc.p, dr.p, dv.p, nar, n, ptr, idx, val));
+    k_spmv_warp<<<(n + kSpmvWarps - 1) / kSpmvWarps, kSpmvWarps * 32>>>(ptr.p, idx.p, val.p, dy.p, dx.p,
+                                                                        one.p, 1.0f, n, nullptr, nullptr);
+    DS_CUDA(cudaMemcpy(x, dx.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  DS_CUDA(cudaGetLastError());
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_lsmr(int m, int n, int leniw, int lenrw, const int *iw, const float *rw,
+                          const float *b, float damp, float atol, float btol, float conlim,
+                          int itnlim, int localSize, float *x, int *istop, int *itn, float *normA,
+                          float *condA, float *normr, float *normAr, float *normx) {
+  if (!iw || !rw || !b || !x || leniw < 1) return DSURF_ERR_BAD_ARG;
+  const long long nar = iw[0];
+  if (leniw < 2 * nar + 1 || lenrw < nar) return DSURF_ERR_BAD_ARG;
+  dsurf_lsmr_sys *sys = nullptr;
+  DS_CHECK(dsurf_lsmr_create(&sys, m, n, nar, iw + 1, iw + 1 + nar, rw, b));
+  int rc = dsurf_lsmr_solve(sys, damp, atol, btol, conlim, itnlim, localSize, 0, x, istop, itn, normA,
+                            condA, normr, normAr, normx, nullptr, nullptr, nullptr);
+  dsurf_lsmr_destroy(sys);
+  return rc;
+}

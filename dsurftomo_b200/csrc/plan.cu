@@ -1,0 +1,726 @@
+// Host orchestration of the forward/sensitivity path, replacing subroutine CalSurfG
+// (src/CalSurfG.f90:939-1459): K1 dispersion + depth kernels per data type, then for batches of
+// (gather, ig) sweeps K2 dicing, K3 eikonal, K4/K5 receiver times + rays, K6 row assembly into a
+// device-resident COO in the reference's row/column order.
+//
+// What the reference redoes per source and this plan hoists (identical values):
+//   * gridder per source (:1186)            -> each velocity map is diced once per model;
+//   * slab copies of sen_* per source (:1146-1168) -> per-type S = sen_vp*coe_a+sen_rho*coe_rho
+//     +sen_vs combined once (same fp64 operation order as :1396-1399);
+//   * dense row(nparpi) zero + scan per ray (:1383,1425) -> ordered compaction of the touched
+//     vertices.
+// Geometry scalars and sin(colatitude) tables are computed on the host in REAL*4 with the C
+// library exactly as the reference computes them, so the device never evaluates a sine on the
+// eikonal path.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../../include/dsurftomo_b200.h"
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace dsurf {
+int launch_coef(cudaStream_t st, const float *d_vels, int nx, int ny, int nz, int brocher, float *coe_a,
+                float *coe_rho);
+int launch_combine(cudaStream_t st, const double *sen_vs, const double *sen_vp, const double *sen_rho,
+                   const float *coe_a, const float *coe_rho, int ncol, int kmax_t, int nzm1, double *S);
+int launch_assembly(cudaStream_t st, const Geom &g, int nz, const float *d_fdm, const int4 *d_bbox, int nrays,
+                    const int *d_ray_S, const double *const *d_S_ptr, const long long *d_S_stride,
+                    const int *d_ray_row, DevBuf<int> &cnt, DevBuf<long long> &wide, DevBuf<long long> &loff,
+                    DevBuf<long long> &roff, DevBuf<int> &lpos, DevBuf<float> &lval, DevBuf<int> &lcnt,
+                    DevBuf<char> &tmp, DevBuf<float> &rw, DevBuf<int> &col, DevBuf<int> &rowidx,
+                    long long &nar, int *d_err, int *launches);
+}  // namespace dsurf
+
+using namespace dsurf;
+
+namespace {
+struct GatherInfo {
+  int knumi, srcnum;  // 1-based loop indices of CalSurfG.f90:1144-1145
+  int type;           // 0 Rc, 1 Rg, 2 Lc, 3 Lg
+  int per;            // periods(srcnum,knumi), 1-based inside the type
+  int igr;            // 0 phase, 1 group
+  int nrc;
+  int first_row;      // 0-based global row of the first receiver
+  float scx, scz;
+};
+struct SweepRef {
+  int gather, ig;
+};
+}  // namespace
+
+struct dsurf_plan {
+  Geom g{};
+  int nz = 0, kmaxT[4] = {0, 0, 0, 0}, kmax = 0, nsrc = 0, nrcf = 0;
+  float minthk = 0;
+  std::vector<float> depz;
+  std::vector<double> tper[4];
+  std::vector<GatherInfo> gathers;
+  std::vector<float> rcx, rcz;  // per gather receivers, flattened by first_row
+  int dall = 0;
+  cudaStream_t st = nullptr;
+  // model + dispersion
+  DevBuf<float> vels, coe_a, coe_rho;
+  LayerTablesDev tables;
+  DevBuf<double> dt[4], pv[4], sen[4][3], S[4], cgbuf;
+  int pvcols[4] = {0, 0, 0, 0};
+  bool disp_done = false;
+  // velocity maps: slot = mapslot[array][col]
+  std::vector<int> mapslot[4];
+  int nmaps = 0;
+  DevBuf<float> velv_all, veln_all, risti_c;
+  bool maps_diced = false;
+  // S table (one entry per (type, period))
+  DevBuf<const double *> S_ptr;
+  DevBuf<long long> S_stride;
+  std::vector<int> S_id_base = std::vector<int>(4, 0);
+  // batch workspace
+  int maxslots = 0, maxrays = 0, hcap = 0;
+  DevBuf<int2> node, noder;
+  DevBuf<float> velr, hkey, ristr;
+  DevBuf<int> hnode;
+  DevBuf<SweepDesc> d_sw;
+  DevBuf<RayDesc> d_rays;
+  DevBuf<float> fdm;
+  DevBuf<int4> bbox;
+  DevBuf<int> ray_S, ray_row;
+  DevBuf<int> cnt, lcnt, lpos;
+  DevBuf<long long> wide, loff, roff;
+  DevBuf<float> lval;
+  DevBuf<char> tmp;
+  // outputs
+  DevBuf<float> dsurf, rw;
+  DevBuf<int> col, rowidx, flags;  // flags[0] err, flags[1] rbint
+  long long nar = 0;
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+static const float kPi = 3.1415926535898f;  // CalSurfG.f90:196
+
+static void make_geom(Geom &g, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd) {
+  g.nx = nx;
+  g.ny = ny;
+  g.nvx = nx - 2;
+  g.nvz = ny - 2;
+  g.earth = 6371.0f;
+  g.dvx = dvxd * kPi / 180.0f;
+  g.dvz = dvzd * kPi / 180.0f;
+  g.gox = (90.0f - goxd) * kPi / 180.0f;
+  g.goz = gozd * kPi / 180.0f;
+  g.nnx = (g.nvx - 1) * kGd + 1;
+  g.nnz = (g.nvz - 1) * kGd + 1;
+  g.dnx = g.dvx / (float)kGd;
+  g.dnz = g.dvz / (float)kGd;
+  g.drnx = g.dvx / (float)(kGd * kSgdl);
+  g.drnz = g.dvz / (float)(kGd * kSgdl);
+  float dpl = g.dnx * g.earth;                        // :1705-1709 / :1864-1869
+  float rd1 = g.dnz * g.earth * sinf(g.gox);
+  if (rd1 < dpl) dpl = rd1;
+  rd1 = g.dnz * g.earth * sinf(g.gox + (float)(g.nnx - 1) * g.dnx);
+  if (rd1 < dpl) dpl = rd1;
+  g.dpl_sr = dpl;
+  g.dpl_ray = 0.5f * dpl;
+  g.x_last = g.gox + (float)(g.nnx - 1) * g.dnx;
+  g.z_last = g.goz + (float)(g.nnz - 1) * g.dnz;
+}
+
+// host part of CalSurfG.f90:1209-1240 + travel's :312-325 + rpaths' :1853-1854 for one source
+static int make_sweep(const Geom &g, float x, float z, SweepDesc &d, float *ristr /*129*/) {
+  int isx = (int)((x - g.gox) / g.dnx) + 1;
+  int isz = (int)((z - g.goz) / g.dnz) + 1;
+  if (isx < 1 || isx > g.nnx || isz < 1 || isz > g.nnz) return DSURF_ERR_SOURCE_OUTSIDE;
+  if (isx == g.nnx) isx = isx - 1;
+  if (isz == g.nnz) isz = isz - 1;
+  d.isx = isx;
+  d.isz = isz;
+  d.scx = x;
+  d.scz = z;
+  d.vnl = std::max(isx - kSgs, 1);
+  d.vnr = std::min(isx + kSgs, g.nnx);
+  d.vnt = std::max(isz - kSgs, 1);
+  d.vnb = std::min(isz + kSgs, g.nnz);
+  d.nrnx = (d.vnr - d.vnl) * kSgdl + 1;
+  d.nrnz = (d.vnb - d.vnt) * kSgdl + 1;
+  d.gorx = g.gox + g.dnx * (float)(d.vnl - 1);
+  d.gorz = g.goz + g.dnz * (float)(d.vnt - 1);
+  int tsx = (int)((x - d.gorx) / g.drnx) + 1;
+  int tsz = (int)((z - d.gorz) / g.drnz) + 1;
+  d.rsx = tsx;
+  d.rsz = tsz;
+  if (tsx < 1 || tsx > d.nrnx || tsz < 1 || tsz > d.nrnz) return DSURF_ERR_SOURCE_OUTSIDE;
+  if (tsx == d.nrnx) tsx = tsx - 1;
+  if (tsz == d.nrnz) tsz = tsz - 1;
+  d.tsx = tsx;
+  d.tsz = tsz;
+  for (int ix = 1; ix <= d.nrnx; ix++) ristr[ix - 1] = g.earth * sinf(d.gorx + (float)(ix - 1) * g.drnx);
+  d.status = 0;
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const float *vels, float goxdf,
+                                 float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                                 int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                                 const double *tLg, const int *wavetype, const int *igrt, const int *periods,
+                                 const float *depz, float minthk, const float *scxf, const float *sczf,
+                                 const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                                 int kmax, int nsrcsurf, int nrcf) {
+  DS_CHECK(ensure_device());
+  if (!out || nx < 4 || ny < 4 || nz < 2 || kmax != kmaxRc + kmaxRg + kmaxLc + kmaxLg) return DSURF_ERR_BAD_ARG;
+  auto *p = new dsurf_plan();
+  make_geom(p->g, nx, ny, goxdf, gozdf, dvxdf, dvzdf);
+  p->nz = nz;
+  p->kmaxT[0] = kmaxRc;
+  p->kmaxT[1] = kmaxRg;
+  p->kmaxT[2] = kmaxLc;
+  p->kmaxT[3] = kmaxLg;
+  p->kmax = kmax;
+  p->nsrc = nsrcsurf;
+  p->nrcf = nrcf;
+  p->minthk = minthk;
+  p->depz.assign(depz, depz + nz);
+  const double *tp[4] = {tRc, tRg, tLc, tLg};
+  for (int t = 0; t < 4; t++)
+    if (p->kmaxT[t] > 0) p->tper[t].assign(tp[t], tp[t] + p->kmaxT[t]);  // never touch t when kmaxX == 0
+  // pv arrays: Rc and Lc are dimensioned with kmax columns in the reference (:1003-1004)
+  p->pvcols[0] = kmax;
+  p->pvcols[1] = std::max(kmaxRg, 1);
+  p->pvcols[2] = kmax;
+  p->pvcols[3] = std::max(kmaxLg, 1);
+  for (int t = 0; t < 4; t++) p->mapslot[t].assign(p->pvcols[t], -1);
+  // ---- flatten the gather loop nest and assign velocity-map slots
+  const int koff[4] = {0, kmaxRc, kmaxRc + kmaxRg, kmaxRc + kmaxRg + kmaxLc};
+  int row = 0;
+  auto slot_of = [&](int arr, int col0) {
+    if (col0 < 0 || col0 >= p->pvcols[arr]) return -1;
+    if (p->mapslot[arr][col0] < 0) p->mapslot[arr][col0] = p->nmaps++;
+    return p->mapslot[arr][col0];
+  };
+  for (int knumi = 1; knumi <= kmax; knumi++) {
+    for (int srcnum = 1; srcnum <= nsrcsurf1[knumi - 1]; srcnum++) {
+      const size_t i2 = (size_t)(knumi - 1) * nsrcsurf + (srcnum - 1);
+      const int wt = wavetype[i2], gr = igrt[i2];
+      int type = -1;
+      if (wt == 2 && gr == 0) type = 0;
+      if (wt == 2 && gr == 1) type = 1;
+      if (wt == 1 && gr == 0) type = 2;
+      if (wt == 1 && gr == 1) type = 3;
+      GatherInfo gi;
+      gi.knumi = knumi;
+      gi.srcnum = srcnum;
+      gi.type = type;
+      gi.per = periods[i2];
+      gi.igr = gr;
+      gi.nrc = nrc1[i2];
+      gi.first_row = row;
+      gi.scx = scxf[i2];
+      gi.scz = sczf[i2];
+      if (type < 0 || gi.per < 1 || gi.per > p->kmaxT[type] || knumi - koff[type] < 1 ||
+          knumi - koff[type] > p->kmaxT[type]) {
+        set_error(__FILE__, __LINE__, "gather wavetype/igrt/periods inconsistent with its knumi block");
+        delete p;
+        return DSURF_ERR_BAD_ARG;
+      }
+      slot_of(type, gi.per - 1);
+      if (gr == 1) slot_of(type == 1 ? 0 : 2, gi.per - 1);  // ig = 2 propagates on the phase map (:1177-1185)
+      for (int r = 0; r < gi.nrc; r++) {
+        const size_t i3 = i2 * nrcf + r;
+        p->rcx.push_back(rcxf[i3]);
+        p->rcz.push_back(rczf[i3]);
+      }
+      row += gi.nrc;
+      p->gathers.push_back(gi);
+    }
+  }
+  p->dall = row;
+  const size_t ncol = (size_t)nx * ny;
+  const size_t Nc = (size_t)p->g.nnx * p->g.nnz;
+  bool bad = false;
+  bad |= p->vels.reserve(ncol * nz) != cudaSuccess;
+  bad |= p->coe_a.reserve(ncol * (nz - 1)) != cudaSuccess;
+  bad |= p->coe_rho.reserve(ncol * (nz - 1)) != cudaSuccess;
+  for (int t = 0; t < 4; t++) {
+    const int kt = p->kmaxT[t];
+    bad |= p->pv[t].reserve(ncol * p->pvcols[t]) != cudaSuccess;
+    if (kt > 0) {
+      bad |= p->dt[t].reserve(kt) != cudaSuccess;
+      for (int q = 0; q < 3; q++) bad |= p->sen[t][q].reserve(ncol * kt * nz) != cudaSuccess;
+      bad |= p->S[t].reserve(ncol * kt * (nz - 1)) != cudaSuccess;
+    }
+  }
+  bad |= p->velv_all.reserve(std::max<size_t>(1, p->nmaps) * ncol) != cudaSuccess;
+  bad |= p->veln_all.reserve(std::max<size_t>(1, p->nmaps) * Nc) != cudaSuccess;
+  bad |= p->risti_c.reserve(p->g.nnx) != cudaSuccess;
+  bad |= p->dsurf.reserve(std::max(1, p->dall)) != cudaSuccess;
+  bad |= p->flags.reserve(4) != cudaSuccess;
+  bad |= p->S_ptr.reserve(std::max(1, kmax)) != cudaSuccess;
+  bad |= p->S_stride.reserve(std::max(1, kmax)) != cudaSuccess;
+  if (bad) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (plan)");
+    delete p;
+    return DSURF_ERR_CUDA;
+  }
+  cudaMemcpy(p->vels.p, vels, ncol * nz * sizeof(float), cudaMemcpyHostToDevice);
+  for (int t = 0; t < 4; t++) {
+    if (p->kmaxT[t] > 0) cudaMemcpy(p->dt[t].p, p->tper[t].data(), p->kmaxT[t] * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(p->pv[t].p, 0, ncol * p->pvcols[t] * sizeof(double));
+  }
+  {
+    std::vector<float> r(p->g.nnx);
+    for (int ix = 1; ix <= p->g.nnx; ix++) r[ix - 1] = p->g.earth * sinf(p->g.gox + (float)(ix - 1) * p->g.dnx);
+    cudaMemcpy(p->risti_c.p, r.data(), r.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  cudaMemset(p->flags.p, 0, 4 * sizeof(int));
+  cudaMemset(p->dsurf.p, 0, std::max(1, p->dall) * sizeof(float));
+  {  // S table: id = koff[type] + (period-1)
+    std::vector<const double *> sp(std::max(1, kmax), nullptr);
+    std::vector<long long> ss(std::max(1, kmax), 0);
+    for (int t = 0; t < 4; t++)
+      for (int c = 0; c < p->kmaxT[t]; c++) {
+        sp[koff[t] + c] = p->S[t].p + (size_t)c * ncol;
+        ss[koff[t] + c] = (long long)p->kmaxT[t] * (long long)ncol;
+      }
+    for (int t = 0; t < 4; t++) p->S_id_base[t] = koff[t];
+    cudaMemcpy(p->S_ptr.p, sp.data(), sp.size() * sizeof(const double *), cudaMemcpyHostToDevice);
+    cudaMemcpy(p->S_stride.p, ss.data(), ss.size() * sizeof(long long), cudaMemcpyHostToDevice);
+  }
+  LayerTables T;
+  make_layer_tables(depz, nz, minthk, T);
+  if (upload_tables(T, p->tables) != DSURF_OK) {
+    delete p;
+    return DSURF_ERR_CUDA;
+  }
+  for (auto &e : p->ev) cudaEventCreate(&e);
+  // ---- batch workspace sizing
+  size_t freeb = 0, totalb = 0;
+  cudaMemGetInfo(&freeb, &totalb);
+  p->hcap = 8 * (p->g.nnx + p->g.nnz) + 1024;
+  const size_t fdm_per_ray = (size_t)(p->g.nvz + 2) * (p->g.nvx + 2) * sizeof(float);
+  int maxnrc = 1;
+  for (auto &gi : p->gathers) maxnrc = std::max(maxnrc, gi.nrc);
+  const size_t per_slot = Nc * sizeof(int2) + (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) +
+                          (size_t)(p->hcap + 1) * 8 + kRefMax * sizeof(float) + sizeof(SweepDesc) +
+                          (size_t)maxnrc * (fdm_per_ray + sizeof(RayDesc) + 64);
+  const size_t budget = std::min<size_t>((size_t)(freeb * 0.55), (size_t)64 << 30);
+  long long nsw_total = 0;
+  for (auto &gi : p->gathers) nsw_total += gi.igr == 1 ? 2 : 1;
+  long long ms = (long long)(budget / per_slot);
+  ms = std::min<long long>(ms, std::max<long long>(nsw_total, 1));
+  ms = std::min<long long>(ms, (long long)sm_count() * 64);
+  ms = std::max<long long>(ms, 1);
+  p->maxslots = (int)ms;
+  p->maxrays = (int)std::min<long long>((long long)p->maxslots * maxnrc, 1ll << 30);
+  bad = false;
+  bad |= p->node.reserve((size_t)p->maxslots * Nc) != cudaSuccess;
+  bad |= p->noder.reserve((size_t)p->maxslots * kRefMax * kRefMax) != cudaSuccess;
+  bad |= p->velr.reserve((size_t)p->maxslots * kRefMax * kRefMax) != cudaSuccess;
+  bad |= p->hkey.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
+  bad |= p->hnode.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
+  bad |= p->ristr.reserve((size_t)p->maxslots * kRefMax) != cudaSuccess;
+  bad |= p->d_sw.reserve(p->maxslots) != cudaSuccess;
+  bad |= p->d_rays.reserve(p->maxrays) != cudaSuccess;
+  bad |= p->fdm.reserve((size_t)p->maxrays * (fdm_per_ray / sizeof(float))) != cudaSuccess;
+  bad |= p->bbox.reserve(p->maxrays) != cudaSuccess;
+  bad |= p->ray_S.reserve(p->maxrays) != cudaSuccess;
+  bad |= p->ray_row.reserve(p->maxrays) != cudaSuccess;
+  if (bad) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (batch workspace)");
+    delete p;
+    return DSURF_ERR_CUDA;
+  }
+  cudaMemset(p->fdm.p, 0, (size_t)p->maxrays * fdm_per_ray);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+    delete p;
+    return DSURF_ERR_CUDA;
+  }
+  *out = p;
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_destroy(dsurf_plan *p) {
+  if (!p) return DSURF_OK;
+  for (auto &e : p->ev)
+    if (e) cudaEventDestroy(e);
+  delete p;
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_set_model(dsurf_plan *p, const float *vels) {
+  if (!p || !vels) return DSURF_ERR_BAD_ARG;
+  DS_CUDA(cudaMemcpy(p->vels.p, vels, (size_t)p->g.nx * p->g.ny * p->nz * sizeof(float), cudaMemcpyHostToDevice));
+  p->disp_done = false;
+  p->maps_diced = false;
+  return DSURF_OK;
+}
+
+static int dice_maps(dsurf_plan *p) {
+  const size_t ncol = (size_t)p->g.nx * p->g.ny, Nc = (size_t)p->g.nnx * p->g.nnz;
+  for (int arr = 0; arr < 4; arr++)
+    for (int c = 0; c < p->pvcols[arr]; c++) {
+      const int s = p->mapslot[arr][c];
+      if (s < 0) continue;
+      DS_CHECK(launch_dice(p->st, p->g, p->pv[arr].p + (size_t)c * ncol, p->velv_all.p + (size_t)s * ncol,
+                           p->veln_all.p + (size_t)s * Nc));
+    }
+  DS_CUDA(cudaGetLastError());
+  p->maps_diced = true;
+  return DSURF_OK;
+}
+
+// CalSurfG.f90:1098-1133 in the reference's call order (pvRc / pvLc overwrite quirk included)
+extern "C" int dsurf_plan_dispersion(dsurf_plan *p) {
+  if (!p) return DSURF_ERR_BAD_ARG;
+  DS_CHECK(ensure_device());
+  const Geom &g = p->g;
+  cudaEventRecord(p->ev[0], p->st);
+  const int iw[4] = {2, 2, 1, 1}, ig[4] = {0, 1, 0, 1};
+  for (int t = 0; t < 4; t++) {
+    const int kt = p->kmaxT[t];
+    if (kt <= 0) continue;
+    if (ig[t] == 1) {  // caldespersion: phase maps at the group periods into pvRc / pvLc
+      const int ph = (t == 1) ? 0 : 2;
+      DS_CHECK(run_dispersion(p->st, p->vels.p, g.nx, g.ny, p->nz, p->tables, iw[t], 0, kt, p->dt[t].p, false,
+                              p->pv[ph].p, nullptr, nullptr, nullptr, p->cgbuf));
+    }
+    DS_CHECK(run_dispersion(p->st, p->vels.p, g.nx, g.ny, p->nz, p->tables, iw[t], ig[t], kt, p->dt[t].p, true,
+                            p->pv[t].p, p->sen[t][0].p, p->sen[t][1].p, p->sen[t][2].p, p->cgbuf));
+  }
+  // coe_a / coe_rho and the combined kernels S (row assembly operands)
+  const int brocher = p->depz[p->nz - 2] < 35.0f ? 1 : 0;  // :1385
+  DS_CHECK(launch_coef(p->st, p->vels.p, g.nx, g.ny, p->nz, brocher, p->coe_a.p, p->coe_rho.p));
+  for (int t = 0; t < 4; t++)
+    if (p->kmaxT[t] > 0)
+      DS_CHECK(launch_combine(p->st, p->sen[t][0].p, p->sen[t][1].p, p->sen[t][2].p, p->coe_a.p, p->coe_rho.p,
+                              g.nx * g.ny, p->kmaxT[t], p->nz - 1, p->S[t].p));
+  cudaEventRecord(p->ev[1], p->st);
+  DS_CHECK(dice_maps(p));
+  cudaEventRecord(p->ev[2], p->st);
+  DS_CUDA(cudaStreamSynchronize(p->st));
+  DS_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+  p->ms[0] = ms;
+  cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]);
+  p->ms[1] = ms;
+  p->disp_done = true;
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_set_map(dsurf_plan *p, int type, int period0, const double *pvh) {
+  if (!p || type < 0 || type > 3 || period0 < 0 || period0 >= p->pvcols[type]) return DSURF_ERR_BAD_ARG;
+  const size_t ncol = (size_t)p->g.nx * p->g.ny;
+  DS_CUDA(cudaMemcpy(p->pv[type].p + (size_t)period0 * ncol, pvh, ncol * sizeof(double), cudaMemcpyHostToDevice));
+  p->maps_diced = false;
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_reset_rows(dsurf_plan *p) {
+  if (!p) return DSURF_ERR_BAD_ARG;
+  p->nar = 0;
+  DS_CUDA(cudaMemset(p->flags.p, 0, 4 * sizeof(int)));
+  return DSURF_OK;
+}
+extern "C" int dsurf_plan_num_gathers(const dsurf_plan *p) { return p ? (int)p->gathers.size() : 0; }
+extern "C" int dsurf_plan_num_sweeps(const dsurf_plan *p, int g0, int g1) {
+  if (!p) return 0;
+  int n = 0;
+  for (int g = std::max(g0, 0); g < std::min(g1, (int)p->gathers.size()); g++) n += p->gathers[g].igr == 1 ? 2 : 1;
+  return n;
+}
+extern "C" int64_t dsurf_plan_nar(const dsurf_plan *p) { return p ? p->nar : 0; }
+extern "C" int dsurf_plan_nrows(const dsurf_plan *p) { return p ? p->dall : 0; }
+
+// runs one batch of sweeps (already described in hsw / hrays); assemble = false keeps fdm
+static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<RayDesc> &hrays,
+                     std::vector<float> &hristr, std::vector<int> &hrayS, std::vector<int> &hrayrow,
+                     bool assemble, int *launches) {
+  const int nsw = (int)hsw.size(), nrays = (int)hrays.size();
+  if (nsw == 0) return DSURF_OK;
+  cudaStream_t st = p->st;
+  DS_CUDA(cudaMemcpyAsync(p->d_sw.p, hsw.data(), nsw * sizeof(SweepDesc), cudaMemcpyHostToDevice, st));
+  DS_CUDA(cudaMemcpyAsync(p->ristr.p, hristr.data(), (size_t)nsw * kRefMax * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (nrays > 0) {
+    DS_CUDA(cudaMemcpyAsync(p->d_rays.p, hrays.data(), nrays * sizeof(RayDesc), cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemcpyAsync(p->ray_S.p, hrayS.data(), nrays * sizeof(int), cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemcpyAsync(p->ray_row.p, hrayrow.data(), nrays * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  float ms;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    BatchView bv;
+    bv.node = p->node.p;
+    bv.noder = p->noder.p;
+    bv.velr = p->velr.p;
+    bv.hkey = p->hkey.p;
+    bv.hnode = p->hnode.p;
+    bv.ristr = p->ristr.p;
+    bv.hcap = p->hcap;
+    cudaEventRecord(p->ev[0], st);
+    DS_CHECK(launch_eikonal(st, p->g, p->d_sw.p, nsw, p->veln_all.p, p->velv_all.p, p->risti_c.p, bv, launches));
+    cudaEventRecord(p->ev[1], st);
+    DS_CUDA(cudaMemcpyAsync(hsw.data(), p->d_sw.p, nsw * sizeof(SweepDesc), cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    DS_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+    p->ms[2] += ms;
+    p->ms[5] += 1;
+    bool heap_err = false;
+    for (auto &s : hsw)
+      if (s.status == DSURF_ERR_HEAP) heap_err = true;
+    if (!heap_err) break;
+    // narrow band larger than the default slab: grow towards the reference's maxbt = 0.5*Nc
+    const long long maxbt = (long long)std::lround(0.5 * (double)p->g.nnx * p->g.nnz);
+    if (p->hcap >= maxbt || attempt == 2) {
+      set_error(__FILE__, __LINE__, "narrow-band heap exceeded maxbt = NINT(0.5*nnx*nnz)");
+      return DSURF_ERR_HEAP;
+    }
+    p->hcap = (int)std::min<long long>(maxbt, (long long)p->hcap * 8);
+    if (p->hkey.reserve((size_t)p->maxslots * (p->hcap + 1)) || p->hnode.reserve((size_t)p->maxslots * (p->hcap + 1))) {
+      set_error(__FILE__, __LINE__, "cudaMalloc failed (heap growth)");
+      return DSURF_ERR_CUDA;
+    }
+    for (auto &s : hsw) s.status = 0;
+    DS_CUDA(cudaMemcpyAsync(p->d_sw.p, hsw.data(), nsw * sizeof(SweepDesc), cudaMemcpyHostToDevice, st));
+  }
+  if (nrays > 0) {
+    BatchView bv;
+    bv.node = p->node.p;
+    bv.noder = p->noder.p;
+    bv.velr = p->velr.p;
+    bv.hkey = p->hkey.p;
+    bv.hnode = p->hnode.p;
+    bv.ristr = p->ristr.p;
+    bv.hcap = p->hcap;
+    cudaEventRecord(p->ev[2], st);
+    DS_CHECK(launch_rays(st, p->g, p->d_sw.p, p->d_rays.p, nrays, p->veln_all.p, bv, p->dsurf.p, p->fdm.p,
+                         p->bbox.p, p->flags.p + 1, p->flags.p));
+    if (launches) *launches += 1;
+    cudaEventRecord(p->ev[3], st);
+    if (assemble) {
+      DS_CHECK(launch_assembly(st, p->g, p->nz, p->fdm.p, p->bbox.p, nrays, p->ray_S.p, p->S_ptr.p,
+                               p->S_stride.p, p->ray_row.p, p->cnt, p->wide, p->loff, p->roff, p->lpos, p->lval,
+                               p->lcnt, p->tmp, p->rw, p->col, p->rowidx, p->nar, p->flags.p, launches));
+    }
+    cudaEventRecord(p->ev[4], st);
+    DS_CUDA(cudaStreamSynchronize(st));
+    DS_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]);
+    p->ms[3] += ms;
+    cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]);
+    p->ms[4] += ms;
+  }
+  return DSURF_OK;
+}
+
+static int append_gather(dsurf_plan *p, int gidx, int only_ig, std::vector<SweepDesc> &hsw,
+                         std::vector<RayDesc> &hrays, std::vector<float> &hristr, std::vector<int> &hrayS,
+                         std::vector<int> &hrayrow) {
+  const GatherInfo &gi = p->gathers[gidx];
+  const int igroup = gi.igr == 1 ? 2 : 1;
+  for (int ig = 1; ig <= igroup; ig++) {
+    if (only_ig && ig != only_ig) continue;
+    SweepDesc d;
+    memset(&d, 0, sizeof(d));
+    hristr.resize(hristr.size() + kRefMax, 0.0f);
+    int rc = make_sweep(p->g, gi.scx, gi.scz, d, hristr.data() + hristr.size() - kRefMax);
+    if (rc != DSURF_OK) return rc;
+    int arr = gi.type;
+    if (ig == 2) arr = (gi.type == 1) ? 0 : 2;
+    d.map = p->mapslot[arr][gi.per - 1];
+    d.gather = gidx;
+    d.first_row = gi.first_row;
+    d.nrc = gi.nrc;
+    d.do_times = (ig == 1) ? 1 : 0;
+    d.do_rays = (gi.igr == 0 || ig == 2) ? 1 : 0;
+    const int slot = (int)hsw.size();
+    hsw.push_back(d);
+    for (int r = 0; r < gi.nrc; r++) {
+      RayDesc rd;
+      rd.sweep = slot;
+      rd.row = gi.first_row + r;
+      rd.rcx = p->rcx[gi.first_row + r];
+      rd.rcz = p->rcz[gi.first_row + r];
+      rd.sin_rcx = sinf(rd.rcx);
+      hrays.push_back(rd);
+      hrayS.push_back(p->S_id_base[gi.type] + (gi.knumi - p->S_id_base[gi.type] - 1));  // sen_*(:,knumi,:)
+      hrayrow.push_back(rd.row);
+    }
+  }
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_sweeps(dsurf_plan *p, int g0, int g1) {
+  if (!p) return DSURF_ERR_BAD_ARG;
+  DS_CHECK(ensure_device());
+  if (!p->maps_diced) DS_CHECK(dice_maps(p));
+  g0 = std::max(g0, 0);
+  g1 = std::min(g1, (int)p->gathers.size());
+  for (int i = 2; i < 8; i++) p->ms[i] = 0;
+  int launches = 0, nsolved = 0;
+  std::vector<SweepDesc> hsw;
+  std::vector<RayDesc> hrays;
+  std::vector<float> hristr;
+  std::vector<int> hrayS, hrayrow;
+  int g = g0;
+  while (g < g1) {
+    hsw.clear();
+    hrays.clear();
+    hristr.clear();
+    hrayS.clear();
+    hrayrow.clear();
+    while (g < g1) {
+      const GatherInfo &gi = p->gathers[g];
+      const int ns = gi.igr == 1 ? 2 : 1;
+      if (!hsw.empty() && ((int)hsw.size() + ns > p->maxslots || (int)hrays.size() + ns * gi.nrc > p->maxrays)) break;
+      DS_CHECK(append_gather(p, g, 0, hsw, hrays, hristr, hrayS, hrayrow));
+      g++;
+    }
+    // group gathers trace rays only in pass 2 and times only in pass 1: drop the unused RayDescs
+    // per sweep inside the kernels via do_times/do_rays (both kept so that rows stay aligned).
+    DS_CHECK(run_batch(p, hsw, hrays, hristr, hrayS, hrayrow, true, &launches));
+    nsolved += (int)hsw.size();
+  }
+  int hflags[4];
+  DS_CUDA(cudaMemcpy(hflags, p->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  p->ms[6] = launches;
+  p->ms[7] = nsolved;
+  if (hflags[0] != 0) return hflags[0];
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_download(dsurf_plan *p, int *iw_rows, float *rw, int *col, float *dsurf, int *rbint) {
+  if (!p) return DSURF_ERR_BAD_ARG;
+  if (p->nar > 0) {
+    if (iw_rows) DS_CUDA(cudaMemcpy(iw_rows, p->rowidx.p, p->nar * sizeof(int), cudaMemcpyDeviceToHost));
+    if (rw) DS_CUDA(cudaMemcpy(rw, p->rw.p, p->nar * sizeof(float), cudaMemcpyDeviceToHost));
+    if (col) DS_CUDA(cudaMemcpy(col, p->col.p, p->nar * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (dsurf && p->dall > 0) DS_CUDA(cudaMemcpy(dsurf, p->dsurf.p, p->dall * sizeof(float), cudaMemcpyDeviceToHost));
+  if (rbint) {
+    int f[4];
+    DS_CUDA(cudaMemcpy(f, p->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    *rbint = f[1];
+  }
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_timings(const dsurf_plan *p, double *ms8) {
+  if (!p || !ms8) return DSURF_ERR_BAD_ARG;
+  for (int i = 0; i < 8; i++) ms8[i] = p->ms[i];
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_get_dispersion(dsurf_plan *p, int type, double *pv, double *sen_vs, double *sen_vp,
+                                         double *sen_rho) {
+  if (!p || type < 0 || type > 3) return DSURF_ERR_BAD_ARG;
+  const size_t ncol = (size_t)p->g.nx * p->g.ny;
+  if (pv) DS_CUDA(cudaMemcpy(pv, p->pv[type].p, ncol * p->pvcols[type] * sizeof(double), cudaMemcpyDeviceToHost));
+  const size_t ns = ncol * p->kmaxT[type] * p->nz;
+  double *dst[3] = {sen_vs, sen_vp, sen_rho};
+  for (int q = 0; q < 3; q++)
+    if (dst[q] && ns > 0) DS_CUDA(cudaMemcpy(dst[q], p->sen[type][q].p, ns * sizeof(double), cudaMemcpyDeviceToHost));
+  return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_debug_sweep(dsurf_plan *p, int gidx, int ig, float *veln, float *ttn, float *ttnr,
+                                      int *nstsr, float *rgeom, float *fdm) {
+  if (!p || gidx < 0 || gidx >= (int)p->gathers.size() || ig < 1 || ig > 2) return DSURF_ERR_BAD_ARG;
+  DS_CHECK(ensure_device());
+  if (!p->maps_diced) DS_CHECK(dice_maps(p));
+  std::vector<SweepDesc> hsw;
+  std::vector<RayDesc> hrays;
+  std::vector<float> hristr;
+  std::vector<int> hrayS, hrayrow;
+  DS_CHECK(append_gather(p, gidx, ig, hsw, hrays, hristr, hrayS, hrayrow));
+  if (hsw.empty()) return DSURF_ERR_BAD_ARG;
+  hsw[0].do_rays = 1;
+  int launches = 0;
+  DS_CHECK(run_batch(p, hsw, hrays, hristr, hrayS, hrayrow, false, &launches));
+  const Geom &g = p->g;
+  const size_t Nc = (size_t)g.nnx * g.nnz;
+  const SweepDesc &d = hsw[0];
+  if (veln) DS_CUDA(cudaMemcpy(veln, p->veln_all.p + (size_t)d.map * Nc, Nc * sizeof(float), cudaMemcpyDeviceToHost));
+  if (ttn) {
+    std::vector<int2> tmp(Nc);
+    DS_CUDA(cudaMemcpy(tmp.data(), p->node.p, Nc * sizeof(int2), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < Nc; i++) memcpy(&ttn[i], &tmp[i].x, 4);
+  }
+  if (ttnr || nstsr) {
+    const size_t nr = (size_t)d.nrnx * d.nrnz;
+    std::vector<int2> tmp(nr);
+    DS_CUDA(cudaMemcpy(tmp.data(), p->noder.p, nr * sizeof(int2), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nr; i++) {
+      if (ttnr) memcpy(&ttnr[i], &tmp[i].x, 4);
+      if (nstsr) nstsr[i] = tmp[i].y;
+    }
+  }
+  if (rgeom) {
+    rgeom[0] = d.gorx;
+    rgeom[1] = d.gorz;
+    rgeom[2] = g.drnx;
+    rgeom[3] = g.drnz;
+    rgeom[4] = (float)d.nrnx;
+    rgeom[5] = (float)d.nrnz;
+  }
+  const size_t fsz = (size_t)(g.nvz + 2) * (g.nvx + 2);
+  if (fdm) DS_CUDA(cudaMemcpy(fdm, p->fdm.p, fsz * hrays.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  DS_CUDA(cudaMemset(p->fdm.p, 0, fsz * hrays.size() * sizeof(float)));
+  return DSURF_OK;
+}
+
+// ------------------------------------------------------------------------------- CalSurfG drop-in
+extern "C" int dsurf_calsurfg(int nx, int ny, int nz, int nparpi, const float *vels, int *iw, float *rw,
+                              int *col, float *dsurf, float goxdf, float gozdf, float dvxdf, float dvzdf,
+                              int kmaxRc, int kmaxRg, int kmaxLc, int kmaxLg, const double *tRc,
+                              const double *tRg, const double *tLc, const double *tLg, const int *wavetype,
+                              const int *igrt, const int *periods, const float *depz, float minthk,
+                              const float *scxf, const float *sczf, const float *rcxf, const float *rczf,
+                              const int *nrc1, const int *nsrcsurf1, int kmax, int nsrcsurf, int nrcf,
+                              int64_t maxnar, int *nar, int *rbint) {
+  (void)nparpi;
+  dsurf_plan *p = nullptr;
+  DS_CHECK(dsurf_plan_create(&p, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, kmaxRg, kmaxLc, kmaxLg, tRc,
+                             tRg, tLc, tLg, wavetype, igrt, periods, depz, minthk, scxf, sczf, rcxf, rczf, nrc1,
+                             nsrcsurf1, kmax, nsrcsurf, nrcf));
+  int rc = dsurf_plan_dispersion(p);
+  if (rc == DSURF_OK) rc = dsurf_plan_reset_rows(p);
+  if (rc == DSURF_OK) rc = dsurf_plan_sweeps(p, 0, dsurf_plan_num_gathers(p));
+  if (rc == DSURF_OK && maxnar >= 0 && p->nar > maxnar) {
+    set_error(__FILE__, __LINE__, "nar exceeds the caller's COO capacity (increase sparsity fraction)");
+    rc = DSURF_ERR_CAPACITY;
+  }
+  if (rc == DSURF_OK) rc = dsurf_plan_download(p, iw ? iw + 1 : nullptr, rw, col, dsurf, rbint);
+  if (rc == DSURF_OK && nar) *nar = (int)p->nar;
+  dsurf_plan_destroy(p);
+  return rc;
+}
+
+extern "C" void dsurf_fatal_(const int *rc);
+
+extern "C" void calsurfg_(const int *nx, const int *ny, const int *nz, const int *nparpi, const float *vels,
+                          int *iw, float *rw, int *col, float *dsurf, const float *goxdf, const float *gozdf,
+                          const float *dvxdf, const float *dvzdf, const int *kmaxRc, const int *kmaxRg,
+                          const int *kmaxLc, const int *kmaxLg, const double *tRc, const double *tRg,
+                          const double *tLc, const double *tLg, const int *wavetype, const int *igrt,
+                          const int *periods, const float *depz, const float *minthk, const float *scxf,
+                          const float *sczf, const float *rcxf, const float *rczf, const int *nrc1,
+                          const int *nsrcsurf1, const int *kmax, const int *nsrcsurf, const int *nrcf, int *nar) {
+  int rbint = 0;
+  // the Fortran caller does not pass its COO capacity (maxnar); it is unchecked in the reference too
+  int rc = dsurf_calsurfg(*nx, *ny, *nz, *nparpi, vels, iw, rw, col, dsurf, *goxdf, *gozdf, *dvxdf, *dvzdf, *kmaxRc,
+                          *kmaxRg, *kmaxLc, *kmaxLg, tRc, tRg, tLc, tLg, wavetype, igrt, periods, depz, *minthk,
+                          scxf, sczf, rcxf, rczf, nrc1, nsrcsurf1, *kmax, *nsrcsurf, *nrcf, -1, nar, &rbint);
+  if (rc != DSURF_OK) dsurf_fatal_(&rc);
+  if (rbint) {  // CalSurfG.f90:1447-1454
+    printf(" Note that at least one two-point ray path\n tracked along the boundary of the model.\n"
+           " This class of path is unlikely to be\n a true path, and it is STRONGLY RECOMMENDED\n"
+           " that you adjust the dimensions of your grid\n to prevent this from occurring.\n");
+  }
+}
+
+// not yet implemented in round 1: device-resident host glue
+extern "C" int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **, dsurf_plan *, const float *, float, float) {
+  set_error(__FILE__, __LINE__, "dsurf_lsmr_create_from_plan: not implemented yet");
+  return DSURF_ERR_BAD_ARG;
+}

@@ -1,0 +1,192 @@
+/*
+ * dsurftomo_b200.h -- C ABI of libdsurf_b200.so, the B200 (sm_100a) implementation of
+ * DSurfTomo's forward/sensitivity + LSMR hot path.
+ *
+ * Two layers:
+ *
+ *  (1) gfortran-convention drop-ins.  Same symbol names, argument order and argument meaning
+ *      as the reference subroutines, every argument by reference, arrays column-major and
+ *      1-based in content, no hidden arguments (there are no CHARACTER dummies).  A
+ *      DSurfTomo build links main.o against this library instead of CalSurfG.o / surfdisp96.o /
+ *      lsmrModule.o / aprod.o and nothing else changes.  On the reference's
+ *      fatal conditions these print the reference's message and exit(1) (Fortran STOP).
+ *
+ *        calsurfg_               replaces  subroutine CalSurfG        src/CalSurfG.f90:939-943
+ *        depthkernel_            replaces  subroutine depthkernel     src/CalSurfG.f90:1-2
+ *        caldespersion_          replaces  subroutine caldespersion   src/CalSurfG.f90:2866-2867
+ *        surfdisp96_             replaces  subroutine surfdisp96      src/surfdisp96.f:52-53
+ *        __lsmrmodule_MOD_lsmr   replaces  LSMRmodule::LSMR           src/lsmrModule.f90:36-38
+ *        aprod_                  replaces  subroutine aprod           src/aprod.f90:7
+ *
+ *  (2) neutral C entry points (dsurf_*): scalars by value, an int status instead of STOP.
+ *      All pointers are HOST pointers unless the name ends in _dev; the callee keeps no
+ *      caller pointer after return.  Status codes below.
+ *
+ * Nothing in this header mentions torch; device memory, streams and NCCL are internal.
+ */
+#ifndef DSURFTOMO_B200_H
+#define DSURFTOMO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  DSURF_OK = 0,
+  DSURF_ERR_SOURCE_OUTSIDE = 1,   /* CalSurfG.f90:317-323,1214-1220: "Source lies outside bounds of model" */
+  DSURF_ERR_RECEIVER_OUTSIDE = 2, /* CalSurfG.f90:1686-1692,1898-1904 */
+  DSURF_ERR_NO_CUDA = 3,          /* no usable sm_100 device: the library has NO CPU fallback */
+  DSURF_ERR_CUDA = 4,             /* a CUDA call failed; dsurf_last_error() has the text */
+  DSURF_ERR_CAPACITY = 5,         /* caller-provided rw/iw/col capacity (maxnar) too small */
+  DSURF_ERR_BAD_ARG = 6,
+  DSURF_ERR_HEAP = 7,             /* narrow-band heap exceeded the reference's maxbt = 0.5*nnx*nnz */
+  DSURF_ERR_NCCL = 8
+};
+
+const char *dsurf_last_error(void);
+/* device selection (default: CUDA device 0, or LOCAL_RANK if set) */
+int dsurf_set_device(int device);
+/* library build info: "sm_100a fmad=off ..." */
+const char *dsurf_build_info(void);
+
+/* ------------------------------------------------------------------ (1) Fortran drop-ins */
+
+void calsurfg_(const int *nx, const int *ny, const int *nz, const int *nparpi, const float *vels,
+               int *iw, float *rw, int *col, float *dsurf, const float *goxdf, const float *gozdf,
+               const float *dvxdf, const float *dvzdf, const int *kmaxRc, const int *kmaxRg,
+               const int *kmaxLc, const int *kmaxLg, const double *tRc, const double *tRg,
+               const double *tLc, const double *tLg, const int *wavetype, const int *igrt,
+               const int *periods, const float *depz, const float *minthk, const float *scxf,
+               const float *sczf, const float *rcxf, const float *rczf, const int *nrc1,
+               const int *nsrcsurf1, const int *kmax, const int *nsrcsurf, const int *nrcf, int *nar);
+
+void depthkernel_(const int *nx, const int *ny, const int *nz, const float *vel, double *pvRc,
+                  double *sen_vsRc, double *sen_vpRc, double *sen_rhoRc, const int *iwave,
+                  const int *igr, const int *kmaxRc, const double *tRc, const float *depz,
+                  const float *minthk);
+
+void caldespersion_(const int *nx, const int *ny, const int *nz, const float *vel, double *pvRc,
+                    const int *iwave, const int *igr, const int *kmaxRc, const double *tRc,
+                    const float *depz, const float *minthk);
+
+void surfdisp96_(const float *thkm, const float *vpm, const float *vsm, const float *rhom,
+                 const int *nlayer, const int *iflsph, const int *iwave, const int *mode,
+                 const int *igr, const int *kmax, const double *t, double *cg);
+
+void __lsmrmodule_MOD_lsmr(const int *m, const int *n, const int *leniw, const int *lenrw,
+                           const int *iw, const float *rw, const float *b, const float *damp,
+                           const float *atol, const float *btol, const float *conlim,
+                           const int *itnlim, const int *localSize, const int *nout, float *x,
+                           int *istop, int *itn, float *normA, float *condA, float *normr,
+                           float *normAr, float *normx);
+
+void aprod_(const int *mode, const int *m, const int *n, float *x, float *y, const int *leniw,
+            const int *lenrw, const int *iw, const float *rw);
+
+/* ------------------------------------------------------------------ (2) neutral C entry points */
+
+/* CalSurfG with an explicit COO capacity (maxnar = spfra*dall*nx*ny*nz in main.f90:287) and a
+ * status instead of STOP.  rbint (may be NULL) receives the ray-boundary warning flag of
+ * CalSurfG.f90:1447-1454. */
+int dsurf_calsurfg(int nx, int ny, int nz, int nparpi, const float *vels, int *iw, float *rw,
+                   int *col, float *dsurf, float goxdf, float gozdf, float dvxdf, float dvzdf,
+                   int kmaxRc, int kmaxRg, int kmaxLc, int kmaxLg, const double *tRc,
+                   const double *tRg, const double *tLc, const double *tLg, const int *wavetype,
+                   const int *igrt, const int *periods, const float *depz, float minthk,
+                   const float *scxf, const float *sczf, const float *rcxf, const float *rczf,
+                   const int *nrc1, const int *nsrcsurf1, int kmax, int nsrcsurf, int nrcf,
+                   int64_t maxnar, int *nar, int *rbint);
+
+/* depthkernel / caldespersion (igr: 0 phase, 1 group; iwave: 1 Love, 2 Rayleigh).
+ * sen_* may all be NULL (dispersion map only == caldespersion). */
+int dsurf_depthkernel(int nx, int ny, int nz, const float *vel, double *pv, double *sen_vs,
+                      double *sen_vp, double *sen_rho, int iwave, int igr, int kmax,
+                      const double *t, const float *depz, float minthk);
+
+/* One layered model (the reference's per-column call).  Batched form: nmodel stacks of
+ * nlayer layers each, thk shared. */
+int dsurf_surfdisp96(const float *thkm, const float *vpm, const float *vsm, const float *rhom,
+                     int nlayer, int iflsph, int iwave, int mode, int igr, int kmax,
+                     const double *t, double *cg);
+int dsurf_surfdisp96_batch(int nmodel, const float *thkm, const float *vpm, const float *vsm,
+                           const float *rhom, int nlayer, int iflsph, int iwave, int igr, int kmax,
+                           const double *t, double *cg /* [nmodel][kmax] */);
+
+int dsurf_lsmr(int m, int n, int leniw, int lenrw, const int *iw, const float *rw, const float *b,
+               float damp, float atol, float btol, float conlim, int itnlim, int localSize,
+               float *x, int *istop, int *itn, float *normA, float *condA, float *normr,
+               float *normAr, float *normx);
+
+int dsurf_aprod(int mode, int m, int n, float *x, float *y, int leniw, int lenrw, const int *iw,
+                const float *rw);
+
+/* ------------------------------------------------------------------ staged / device-resident API
+ * Used by bench.py and the stage-level parity tests: the same kernels the drop-ins run, with
+ * inputs kept resident in HBM and per-stage CUDA-event timings. */
+
+typedef struct dsurf_plan dsurf_plan;
+
+/* Uploads model, geometry and the gather tables (same arrays as dsurf_calsurfg). */
+int dsurf_plan_create(dsurf_plan **plan, int nx, int ny, int nz, const float *vels, float goxdf,
+                      float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                      int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                      const double *tLg, const int *wavetype, const int *igrt, const int *periods,
+                      const float *depz, float minthk, const float *scxf, const float *sczf,
+                      const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                      int kmax, int nsrcsurf, int nrcf);
+int dsurf_plan_destroy(dsurf_plan *plan);
+/* replace the model (vels[nz][ny][nx]) for the next outer iteration */
+int dsurf_plan_set_model(dsurf_plan *plan, const float *vels);
+/* K1: dispersion maps + depth kernels for every data type (CalSurfG.f90:1098-1133) */
+int dsurf_plan_dispersion(dsurf_plan *plan);
+/* test hook: overwrite the velocity map (nx*ny doubles) of period-type slot `map` */
+int dsurf_plan_set_map(dsurf_plan *plan, int type /*0 Rc,1 Rg,2 Lc,3 Lg*/, int period0, const double *pv);
+/* K2-K6 for gathers [g0, g1) of the flattened (knumi, srcnum) loop nest; results are appended
+ * to the plan's device COO / dsurf buffers in reference order.  dsurf_plan_reset_rows() rewinds. */
+int dsurf_plan_reset_rows(dsurf_plan *plan);
+int dsurf_plan_sweeps(dsurf_plan *plan, int g0, int g1);
+int dsurf_plan_num_gathers(const dsurf_plan *plan);
+int dsurf_plan_num_sweeps(const dsurf_plan *plan, int g0, int g1);
+int64_t dsurf_plan_nar(const dsurf_plan *plan);
+int dsurf_plan_nrows(const dsurf_plan *plan);
+/* download everything produced so far (any pointer may be NULL) */
+int dsurf_plan_download(dsurf_plan *plan, int *iw_rows /* nar */, float *rw, int *col, float *dsurf,
+                        int *rbint);
+/* stage-level outputs for parity tests: last solved sweep of gather g, pass ig (1 or 2) */
+int dsurf_plan_debug_sweep(dsurf_plan *plan, int g, int ig, float *veln, float *ttn, float *ttnr,
+                           int *nstsr, float *rgeom, float *fdm /* [nrc][nx][ny] or NULL */);
+/* copy device dispersion results to the host (any pointer may be NULL) */
+int dsurf_plan_get_dispersion(dsurf_plan *plan, int type, double *pv, double *sen_vs, double *sen_vp,
+                              double *sen_rho);
+/* timings (ms, CUDA events on the plan's stream) of the last call of each stage:
+ * [0] dispersion, [1] dice, [2] eikonal (refined+coarse FMM), [3] receivers+rays,
+ * [4] row assembly, [5] eikonal launches, [6] total kernel launches of last sweeps call,
+ * [7] sweeps solved in the last call */
+int dsurf_plan_timings(const dsurf_plan *plan, double *ms8);
+
+/* Device-resident LSMR: build from host COO once, then run iterations with everything in HBM. */
+typedef struct dsurf_lsmr_sys dsurf_lsmr_sys;
+int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar, const int *rows1,
+                      const int *cols1, const float *vals, const float *b);
+/* same, taking the COO a plan holds in HBM plus device-side host glue (main.f90:361-466) */
+int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **sys, dsurf_plan *plan, const float *obst,
+                                float threshold0, float weight);
+int dsurf_lsmr_destroy(dsurf_lsmr_sys *sys);
+/* multi-GPU: rows are partitioned over ranks; comm is an ncclComm_t created by the host side
+ * (see dsurftomo_b200/dist.py); the per-iteration exchange is one all-reduce of n+1 floats. */
+int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *nccl_comm, int rank, int nranks);
+int dsurf_nccl_unique_id(void *id128);
+int dsurf_nccl_comm_init(void **comm, const void *id128, int rank, int nranks);
+int dsurf_nccl_comm_destroy(void *comm);
+/* run; max_iters<=0 -> itnlim.  force_iters != 0 disables the stopping tests (benchmarks). */
+int dsurf_lsmr_solve(dsurf_lsmr_sys *sys, float damp, float atol, float btol, float conlim,
+                     int itnlim, int localSize, int force_iters, float *x_host, int *istop, int *itn,
+                     float *normA, float *condA, float *normr, float *normAr, float *normx,
+                     double *ms_total, double *ms_spmv, double *ms_spmtv);
+int64_t dsurf_lsmr_nnz(const dsurf_lsmr_sys *sys);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
