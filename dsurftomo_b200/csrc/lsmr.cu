@@ -337,6 +337,19 @@ __global__ void k_sumsq(const float *x, long long n, double *partial) {
   }
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
+// dist: reduce partials into one device double (then all-reduced by NCCL)
+__global__ void k_reduce_to(double *out, const double *partial, int np) {
+  const double s = block_reduce_partials(partial, np);
+  if (threadIdx.x == 0) *out = s;
+}
+// dist: v = (-beta) v + (1/beta) * vpart   (vpart = all-reduced A'u_raw)
+__global__ void k_combine_v(const LsmrScalars *S, float *v, const float *vpart, int n) {
+  if (S->stop || !S->beta_pos) return;
+  const float nb = S->neg_beta, ib = S->inv_beta;
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot)
+    v[i] = nb * v[i] + ib * vpart[i];
+}
 __global__ void k_init_beta(LsmrScalars *S, const double *partial, int np, const double *extra) {
   double s = block_reduce_partials(partial, np);
   if (threadIdx.x == 0) {
@@ -606,12 +619,25 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   DS_CUDA(cudaMemsetAsync(s->v.p, 0, (size_t)n * sizeof(float), st));
   cudaEventRecord(e0, st);
   // ---- u = b ; beta = ||u|| ; u /= beta ; v = A'u ; alpha = ||v|| ; v /= alpha (:380-397)
+  const bool dist = s->comm != nullptr && s->nranks > 1;
   k_sumsq<<<gvecm, 256, 0, st>>>(s->b.p, m, part);
-  k_init_beta<<<1, 1024, 0, st>>>(S, part, gvecm, nullptr);
+  if (dist) {
+    k_reduce_to<<<1, 1024, 0, st>>>(s->red.p, part, gvecm);
+    DS_CHECK(lsmr_allreduce(s->comm, nullptr, 0, s->red.p, 1, st));
+  }
+  k_init_beta<<<1, 1024, 0, st>>>(S, part, gvecm, dist ? s->red.p : nullptr);
   k_init_scale_copy<<<gvecm, 256, 0, st>>>(s->u.p, s->b.p, nullptr, &S->inv_beta, m);
-  k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
-                                              nullptr, 0.0f, n, part, nullptr);
-  k_init_alpha<<<1, 1024, 0, st>>>(S, part, gv, localVecs);
+  if (!dist) {
+    k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
+                                                nullptr, 0.0f, n, part, nullptr);
+    k_init_alpha<<<1, 1024, 0, st>>>(S, part, gv, localVecs);
+  } else {
+    k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
+                                                nullptr, 0.0f, n, nullptr, nullptr);
+    DS_CHECK(lsmr_allreduce(s->comm, s->v.p, n, nullptr, 0, st));
+    k_sumsq<<<gvec, 256, 0, st>>>(s->v.p, n, part);
+    k_init_alpha<<<1, 1024, 0, st>>>(S, part, gvec, localVecs);
+  }
   k_init_scale_copy<<<gvec, 256, 0, st>>>(s->v.p, s->v.p, s->h.p, &S->inv_alpha, n);
   if (localVecs > 0)
     DS_CUDA(cudaMemcpyAsync(s->localV.p, s->v.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -625,14 +651,28 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
     k_spmv_warp<<<gu, kSpmvWarps * 32, 0, st>>>(s->row_ptr.p, s->csr_col.p, s->csr_val.p, s->v.p, s->u.p,
                                                 &S->alpha, -1.0f, m, part, &S->stop);
     cudaEventRecord(eb, st);
-    k_beta<<<1, 1024, 0, st>>>(S, part, gu, nullptr);
-    if (localVecs > 0) k_enqueue_ptr<<<1, 1, 0, st>>>(S, localVecs);
-    k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
-    // v = A'u - beta v (:495-497)
-    cudaEventRecord(ec, st);
-    k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
-                                                &S->neg_beta, 1.0f, n, nullptr, &S->stop);
-    cudaEventRecord(ed, st);
+    if (!dist) {
+      k_beta<<<1, 1024, 0, st>>>(S, part, gu, nullptr);
+      if (localVecs > 0) k_enqueue_ptr<<<1, 1, 0, st>>>(S, localVecs);
+      k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+      // v = A'u - beta v (:495-497)
+      cudaEventRecord(ec, st);
+      k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
+                                                  &S->neg_beta, 1.0f, n, nullptr, &S->stop);
+      cudaEventRecord(ed, st);
+    } else {
+      // one fused exchange per iteration: partial A'u_raw (n floats) + partial ||u||^2 (1 double)
+      k_reduce_to<<<1, 1024, 0, st>>>(s->red.p, part, gu);
+      cudaEventRecord(ec, st);
+      k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p,
+                                                  s->vpart.p, nullptr, 0.0f, n, nullptr, &S->stop);
+      cudaEventRecord(ed, st);
+      DS_CHECK(lsmr_allreduce(s->comm, s->vpart.p, n, s->red.p, 1, st));
+      k_beta<<<1, 1024, 0, st>>>(S, part, gu, s->red.p);
+      if (localVecs > 0) k_enqueue_ptr<<<1, 1, 0, st>>>(S, localVecs);
+      k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+      k_combine_v<<<gvec, 256, 0, st>>>(S, s->v.p, s->vpart.p, n);
+    }
     // local reorthogonalisation + alpha (:498-504, 731-748); steps beyond the current limit no-op
     const int maxsteps = localVecs;  // c = 0..limit, limit <= localVecs
     for (int c = 0; c <= maxsteps; c++) {

@@ -6,8 +6,7 @@
 // vertex accumulators of the current vertex cell are kept in registers and spilled to the ray's
 // dense fdm(0:nvz+1,0:nvx+1) slab only when the ray enters another vertex cell, so the fp32
 // accumulation order per vertex is exactly the reference's step order.  sin(colatitude) at ray
-// points is evaluated in fp64 and rounded (correctly-rounded fp32 sine, matching glibc's sinf
-// except in vanishingly rare half-ulp cases); all other arithmetic is fp32 in source order.
+// points restates glibc's sinf algorithm (see sin_cr); all other arithmetic is fp32 in source order.
 // K6: ordered compaction: rows come out ascending in column (depth-major, then z, then x
 // vertex) exactly as the reference's scan nn = 1..nparpi emits them.
 // Bound: L2 gather latency (rays), HBM streaming of sen/fdm/CSR (assembly).
@@ -25,7 +24,48 @@ __device__ __forceinline__ void bsp4(float u, float o[4]) {  // CalSurfG.f90:218
   o[2] = (1.0f + 3.0f * u + 3.0f * (u * u) - 3.0f * cube_r(u)) / 6.0f;
   o[3] = cube_r(u) / 6.0f;
 }
-__device__ __forceinline__ float sin_cr(float x) { return (float)sin((double)x); }
+// REAL*4 SIN as the reference's runtime evaluates it.  gfortran's SIN(real(4)) is glibc's sinf,
+// which is NOT correctly rounded (0.85 % of inputs differ from the rounded fp64 sine), so the
+// published algorithm glibc >= 2.28 uses (Arm Optimized Routines sinf: fp64 range reduction by
+// pi/2 and two short fp64 polynomials) is restated here; on the build host it agrees with
+// sinf() bit for bit on all 7.97e7 floats of [2^-7, 6) (checked exhaustively).
+// Evaluated in fp64 without FMA contraction (--fmad=false), like glibc's generic build.
+__device__ __forceinline__ float sinf_poly(double x, double x2, int tab, int n) {
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  if ((n & 1) == 0) {
+    const double x3 = x * x2;
+    const double s1 = S2 + x2 * S3;
+    const double x7 = x3 * x2;
+    const double s = x + x3 * S1;
+    return (float)(s + x7 * s1);
+  }
+  const double sg = tab ? -1.0 : 1.0;
+  const double C0 = sg * 0x1p0, C1 = sg * -0x1.ffffffd0c621cp-2, C2 = sg * 0x1.55553e1068f19p-5,
+               C3 = sg * -0x1.6c087e89a359dp-10, C4 = sg * 0x1.99343027bf8c3p-16;
+  const double x4 = x2 * x2;
+  const double c2 = C3 + x2 * C4;
+  const double c1 = C0 + x2 * C1;
+  const double x6 = x4 * x2;
+  const double c = c1 + x4 * C2;
+  return (float)(c + x6 * c2);
+}
+__device__ __forceinline__ float sin_cr(float y) {
+  const double x = (double)y;
+  const unsigned top = (__float_as_uint(y) >> 20) & 0x7ff;
+  if (top < (0x3f490fdbu >> 20)) {  // |y| < pi/4
+    if (top < (0x39800000u >> 20)) return y;
+    return sinf_poly(x, x * x, 0, 0);
+  }
+  if (top < (0x42f00000u >> 20)) {  // |y| < 120
+    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const double r = x * hpi_inv;
+    const int n = ((int)r + 0x800000) >> 24;
+    const double xr = x - (double)n * hpi;
+    const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    return sinf_poly(xr * sgn, xr * xr, (n & 2) ? 1 : 0, n);
+  }
+  return (float)sin(x);  // outside any colatitude; not reached
+}
 
 __device__ __forceinline__ float node_t(const int2 *n, size_t i) { return __int_as_float(n[i].x); }
 

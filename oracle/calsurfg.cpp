@@ -84,57 +84,41 @@ extern "C" int oracle_sweep_rays(int nx, int ny, float goxd, float gozd, float d
   return 0;
 }
 
-extern "C" int oracle_calsurfg(int nx, int ny, int nz, int nparpi, const float *vels, int *iw,
-                               float *rw, int *col, float *dsurf, float goxdf, float gozdf,
-                               float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
-                               int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
-                               const double *tLg, const int *wavetype, const int *igrt,
-                               const int *periods, const float *depz, float minthk,
-                               const float *scxf, const float *sczf, const float *rcxf,
-                               const float *rczf, const int *nrc1, const int *nsrcsurf1, int kmax,
-                               int nsrcsurf, int nrcf, int *nar_out, int nthreads, int mode,
-                               int *rbint_out, double *stage_seconds) {
-  (void)nparpi;
+namespace {
+// gather loop of CalSurfG (:1135-1456) on given dispersion results.  pv[t] / sen[t][q] per type
+// t = Rc,Rg,Lc,Lg (pv of Rc/Lc have kmax columns, see :1003-1004), q = vs,vp,rho.
+// Only gathers [g_lo, g_hi) of the flattened (knumi, srcnum) nest are evaluated (g_hi < 0: all);
+// rows are numbered globally as in a full run.
+int calsurfg_core(int nx, int ny, int nz, const float *vels, int *iw, float *rw, int *col, float *dsurf,
+                  float goxdf, float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                  int kmaxLg, const double *const pvp[4], const double *const senp[4][3], const int *wavetype,
+                  const int *igrt, const int *periods, const float *depz, const float *scxf, const float *sczf,
+                  const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1, int kmax,
+                  int nsrcsurf, int nrcf, int *nar_out, int nthreads, int mode, int *rbint_out,
+                  double *stage_seconds, int g_lo, int g_hi, double t_disp) {
   const float ftol = 1e-4f;  // CalSurfG.f90:1029
   const size_t ncol = (size_t)nx * ny;
   const int nvx = nx - 2, nvz = ny - 2;
   if (nthreads < 1) nthreads = 1;
-  auto t0 = clk::now();
-  // ---- dispersion maps and depth kernels, :1098-1133.  pvRc/pvLc are dimensioned with kmax
-  // columns because caldespersion overwrites their leading kmaxRg/kmaxLg columns (:1110,1128).
-  std::vector<double> pvRc(ncol * std::max(kmax, 1), 0.0), pvRg(ncol * std::max(kmaxRg, 1), 0.0),
-      pvLc(ncol * std::max(kmax, 1), 0.0), pvLg(ncol * std::max(kmaxLg, 1), 0.0);
-  std::vector<double> sRc[3], sRg[3], sLc[3], sLg[3];
-  for (int q = 0; q < 3; q++) {
-    sRc[q].assign(ncol * std::max(kmaxRc, 1) * nz, 0.0);
-    sRg[q].assign(ncol * std::max(kmaxRg, 1) * nz, 0.0);
-    sLc[q].assign(ncol * std::max(kmaxLc, 1) * nz, 0.0);
-    sLg[q].assign(ncol * std::max(kmaxLg, 1) * nz, 0.0);
-  }
-  if (kmaxRc > 0)
-    oracle_depthkernel(nx, ny, nz, vels, pvRc.data(), sRc[0].data(), sRc[1].data(), sRc[2].data(), 2, 0,
-                       kmaxRc, tRc, depz, minthk, nthreads);
-  if (kmaxRg > 0) {
-    oracle_caldespersion(nx, ny, nz, vels, pvRc.data(), 2, 0, kmaxRg, tRg, depz, minthk, nthreads);
-    oracle_depthkernel(nx, ny, nz, vels, pvRg.data(), sRg[0].data(), sRg[1].data(), sRg[2].data(), 2, 1,
-                       kmaxRg, tRg, depz, minthk, nthreads);
-  }
-  if (kmaxLc > 0)
-    oracle_depthkernel(nx, ny, nz, vels, pvLc.data(), sLc[0].data(), sLc[1].data(), sLc[2].data(), 1, 0,
-                       kmaxLc, tLc, depz, minthk, nthreads);
-  if (kmaxLg > 0) {
-    oracle_caldespersion(nx, ny, nz, vels, pvLc.data(), 1, 0, kmaxLg, tLg, depz, minthk, nthreads);
-    oracle_depthkernel(nx, ny, nz, vels, pvLg.data(), sLg[0].data(), sLg[1].data(), sLg[2].data(), 1, 1,
-                       kmaxLg, tLg, depz, minthk, nthreads);
-  }
+  const double *pvRc = pvp[0], *pvRg = pvp[1], *pvLc = pvp[2], *pvLg = pvp[3];
+  const double *const *sRc = senp[0], *const *sRg = senp[1], *const *sLc = senp[2], *const *sLg = senp[3];
   auto t1 = clk::now();
   const int kmax1 = kmaxRc, kmax2 = kmaxRc + kmaxRg, kmax3 = kmaxRc + kmaxRg + kmaxLc;
 
   // ---- flatten the (knumi, srcnum) loop nest of :1144-1145
   struct Gather { int knumi, srcnum; };
   std::vector<Gather> gathers;
-  for (int knumi = 1; knumi <= kmax; knumi++)
-    for (int srcnum = 1; srcnum <= nsrcsurf1[knumi - 1]; srcnum++) gathers.push_back({knumi, srcnum});
+  std::vector<int> grow;  // first global row of each gather
+  {
+    int row = 0;
+    for (int knumi = 1; knumi <= kmax; knumi++)
+      for (int srcnum = 1; srcnum <= nsrcsurf1[knumi - 1]; srcnum++) {
+        gathers.push_back({knumi, srcnum});
+        grow.push_back(row);
+        row += nrc1[(size_t)(knumi - 1) * nsrcsurf + (srcnum - 1)];
+      }
+  }
+  const long gl = g_lo < 0 ? 0 : g_lo, gh = (g_hi < 0 || g_hi > (long)gathers.size()) ? (long)gathers.size() : g_hi;
   std::vector<RowOut> outs(gathers.size());
   int err = 0, rbint = 0;
   double fmm_s = 0, ray_s = 0;
@@ -157,12 +141,12 @@ extern "C" int oracle_calsurfg(int nx, int ny, int nz, int nparpi, const float *
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
 #endif
-    for (long g = 0; g < (long)gathers.size(); g++) {
+    for (long g = gl; g < gh; g++) {
       const int knumi = gathers[g].knumi, srcnum = gathers[g].srcnum;
       const int wt = wavetype[I2(srcnum, knumi)], gr = igrt[I2(srcnum, knumi)];
       const int per = periods[I2(srcnum, knumi)];
       const double *velf = nullptr;
-      const std::vector<double> *sen = nullptr;  // [0]=vs [1]=vp [2]=rho of this type
+      const double *const *sen = nullptr;  // [0]=vs [1]=vp [2]=rho of this type
       int koff = 0, ktype = 1;
       if (wt == 2 && gr == 0) { velf = &pvRc[(size_t)(per - 1) * ncol]; sen = sRc; koff = 0; ktype = kmaxRc; }
       if (wt == 2 && gr == 1) { velf = &pvRg[(size_t)(per - 1) * ncol]; sen = sRg; koff = kmax1; ktype = kmaxRg; }
@@ -260,9 +244,10 @@ extern "C" int oracle_calsurfg(int nx, int ny, int nz, int nparpi, const float *
   }
   auto t2 = clk::now();
   // ---- ordered concatenation: count1 / count11 / nar bookkeeping of :1135-1136,1369-1431
-  int nar = 0, count1 = 0;
-  for (size_t g = 0; g < gathers.size(); g++) {
+  int nar = 0;
+  for (long g = gl; g < gh; g++) {
     RowOut &o = outs[g];
+    int count1 = grow[g];
     int count11 = count1;
     for (float t : o.tt) dsurf[count1++] = t;
     size_t p = 0;
@@ -279,7 +264,7 @@ extern "C" int oracle_calsurfg(int nx, int ny, int nz, int nparpi, const float *
   *nar_out = nar;
   if (rbint_out) *rbint_out = rbint;
   if (stage_seconds) {
-    stage_seconds[0] = secs(t0, t1);
+    stage_seconds[0] = t_disp;
     stage_seconds[1] = secs(t1, t2);
     stage_seconds[2] = fmm_s;
     stage_seconds[3] = ray_s;
@@ -287,4 +272,79 @@ extern "C" int oracle_calsurfg(int nx, int ny, int nz, int nparpi, const float *
     stage_seconds[5] = (double)nrays;
   }
   return err;
+}
+}  // namespace
+
+extern "C" int oracle_calsurfg(int nx, int ny, int nz, int nparpi, const float *vels, int *iw,
+                               float *rw, int *col, float *dsurf, float goxdf, float gozdf,
+                               float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                               int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                               const double *tLg, const int *wavetype, const int *igrt,
+                               const int *periods, const float *depz, float minthk,
+                               const float *scxf, const float *sczf, const float *rcxf,
+                               const float *rczf, const int *nrc1, const int *nsrcsurf1, int kmax,
+                               int nsrcsurf, int nrcf, int *nar_out, int nthreads, int mode,
+                               int *rbint_out, double *stage_seconds) {
+  (void)nparpi;
+  const size_t ncol = (size_t)nx * ny;
+  if (nthreads < 1) nthreads = 1;
+  auto t0 = clk::now();
+  // ---- dispersion maps and depth kernels, :1098-1133.  pvRc/pvLc are dimensioned with kmax
+  // columns because caldespersion overwrites their leading kmaxRg/kmaxLg columns (:1110,1128).
+  std::vector<double> pvRc(ncol * std::max(kmax, 1), 0.0), pvRg(ncol * std::max(kmaxRg, 1), 0.0),
+      pvLc(ncol * std::max(kmax, 1), 0.0), pvLg(ncol * std::max(kmaxLg, 1), 0.0);
+  std::vector<double> sRc[3], sRg[3], sLc[3], sLg[3];
+  for (int q = 0; q < 3; q++) {
+    sRc[q].assign(ncol * std::max(kmaxRc, 1) * nz, 0.0);
+    sRg[q].assign(ncol * std::max(kmaxRg, 1) * nz, 0.0);
+    sLc[q].assign(ncol * std::max(kmaxLc, 1) * nz, 0.0);
+    sLg[q].assign(ncol * std::max(kmaxLg, 1) * nz, 0.0);
+  }
+  if (kmaxRc > 0)
+    oracle_depthkernel(nx, ny, nz, vels, pvRc.data(), sRc[0].data(), sRc[1].data(), sRc[2].data(), 2, 0,
+                       kmaxRc, tRc, depz, minthk, nthreads);
+  if (kmaxRg > 0) {
+    oracle_caldespersion(nx, ny, nz, vels, pvRc.data(), 2, 0, kmaxRg, tRg, depz, minthk, nthreads);
+    oracle_depthkernel(nx, ny, nz, vels, pvRg.data(), sRg[0].data(), sRg[1].data(), sRg[2].data(), 2, 1,
+                       kmaxRg, tRg, depz, minthk, nthreads);
+  }
+  if (kmaxLc > 0)
+    oracle_depthkernel(nx, ny, nz, vels, pvLc.data(), sLc[0].data(), sLc[1].data(), sLc[2].data(), 1, 0,
+                       kmaxLc, tLc, depz, minthk, nthreads);
+  if (kmaxLg > 0) {
+    oracle_caldespersion(nx, ny, nz, vels, pvLc.data(), 1, 0, kmaxLg, tLg, depz, minthk, nthreads);
+    oracle_depthkernel(nx, ny, nz, vels, pvLg.data(), sLg[0].data(), sLg[1].data(), sLg[2].data(), 1, 1,
+                       kmaxLg, tLg, depz, minthk, nthreads);
+  }
+  const double *pvp[4] = {pvRc.data(), pvRg.data(), pvLc.data(), pvLg.data()};
+  const double *senp[4][3];
+  for (int q = 0; q < 3; q++) {
+    senp[0][q] = sRc[q].data();
+    senp[1][q] = sRg[q].data();
+    senp[2][q] = sLc[q].data();
+    senp[3][q] = sLg[q].data();
+  }
+  return calsurfg_core(nx, ny, nz, vels, iw, rw, col, dsurf, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, kmaxRg, kmaxLc,
+                       kmaxLg, pvp, senp, wavetype, igrt, periods, depz, scxf, sczf, rcxf, rczf, nrc1, nsrcsurf1,
+                       kmax, nsrcsurf, nrcf, nar_out, nthreads, mode, rbint_out, stage_seconds, -1, -1,
+                       secs(t0, clk::now()));
+}
+
+// Same gather loop on caller-provided dispersion results (bench.py's CPU arm: the sweep stage
+// without re-running the dispersion stage).  pv/sen layouts as oracle_depthkernel.
+extern "C" int oracle_calsurfg_pre(int nx, int ny, int nz, const float *vels, int *iw, float *rw, int *col,
+                                   float *dsurf, float goxdf, float gozdf, float dvxdf, float dvzdf, int kmaxRc,
+                                   int kmaxRg, int kmaxLc, int kmaxLg, const double *const *pv4,
+                                   const double *const *sen12, const int *wavetype, const int *igrt,
+                                   const int *periods, const float *depz, const float *scxf, const float *sczf,
+                                   const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                                   int kmax, int nsrcsurf, int nrcf, int *nar, int nthreads, int mode,
+                                   int *rbint_out, double *stage_seconds, int g_lo, int g_hi) {
+  const double *pvp[4] = {pv4[0], pv4[1], pv4[2], pv4[3]};
+  const double *senp[4][3];
+  for (int t = 0; t < 4; t++)
+    for (int q = 0; q < 3; q++) senp[t][q] = sen12[t * 3 + q];
+  return calsurfg_core(nx, ny, nz, vels, iw, rw, col, dsurf, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, kmaxRg, kmaxLc,
+                       kmaxLg, pvp, senp, wavetype, igrt, periods, depz, scxf, sczf, rcxf, rczf, nrc1, nsrcsurf1,
+                       kmax, nsrcsurf, nrcf, nar, nthreads, mode, rbint_out, stage_seconds, g_lo, g_hi, 0.0);
 }

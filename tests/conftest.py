@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA (B200) device; run with -m gpu")
+    config.addinivalue_line("markers", "slow: longer CPU test (still part of the default CPU suite)")
 
 
 def has_gpu():

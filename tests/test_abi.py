@@ -1,0 +1,62 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/dsurftomo_b200.h declares, and fails loudly (no CPU fallback) when no GPU is present."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+from dsurftomo_b200 import _lib, api, inputs
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "dsurftomo_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b(?:int|void|int64_t|const char \*)\s*\*?\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(", txt)
+    return sorted(set(n for n in names if n.startswith(("dsurf_", "__lsmr")) or n.endswith("_")))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(_lib.EXPORTED_SYMBOLS) <= set(syms) | {"dsurf_fatal_"}
+
+
+def test_gfortran_mangled_dropins_present():
+    L = _lib.lib()
+    for s in ("calsurfg_", "depthkernel_", "caldespersion_", "surfdisp96_", "aprod_", "__lsmrmodule_MOD_lsmr"):
+        assert hasattr(L, s)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    pb = inputs.synthetic_problem(8, 1, 2, ("Rc",), nrecv=1)
+    with pytest.raises(api.DsurfError) as e:
+        api.CalSurfG(pb)
+    assert e.value.code == 3  # DSURF_ERR_NO_CUDA
+    with pytest.raises(api.DsurfError):
+        api.LSMR(2, 2, 5, 2, np.array([2, 1, 2, 1, 2], np.int32), np.ones(2, np.float32), np.ones(2, np.float32),
+                 0.0, 1e-6, 1e-6, 100.0, 10, 2)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dsurftomo_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)
+
+
+def test_synthetic_generator_shapes():
+    pb = inputs.synthetic_problem(12, 3, 6, ("Rc", "Rg", "Lc", "Lg"), nrecv=5)
+    assert pb.kmax == 12 and pb.ngathers == 72 and pb.dall == 72 * 5
+    assert pb.nsweeps == 3 * 6 * (1 + 2 + 1 + 2)
+    assert pb.scxf.shape == (12, 6) and pb.rcxf.shape == (12, 6, 6)
+    # periods are 1-based indices inside each type; blocks are ordered Rc, Rg, Lc, Lg
+    assert np.array_equal(pb.wavetype[:, 0], [2] * 6 + [1] * 6)
+    assert np.array_equal(pb.igrt[:, 0], [0] * 3 + [1] * 3 + [0] * 3 + [1] * 3)
