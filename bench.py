@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- DSurfTomo hot path on B200: FMM source-period sweeps/s (+ LSMR iterations/s).
+
+One "step" = the sweep stage of CalSurfG (CalSurfG.f90:1186-1432: B-spline dicing, refined +
+coarse eikonal solve, receiver times, ray tracing, Frechet row assembly) over one block of the
+workload: all periods x all sources of one data type of BASELINE.json configs[2]
+(1025 x 1025 propagation grid, 16 periods x (Rc, Rg, Lc, Lg) x 256 sources, 16 receivers per
+gather).  Four consecutive steps are exactly one CalSurfG sweep stage (24 576 sweeps).  The
+dispersion stage feeding it is replaced by deterministic synthetic maps/kernels of the same
+shape (dsurftomo_b200.inputs.synthetic_dispersion) so that the GPU arm and the CPU reference arm
+consume identical inputs; "data": "synthetic".
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (one process per GPU)
+  python bench.py --impl reference ...                      CPU restatement of the reference
+
+See the JSON keys documented in DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from dsurftomo_b200 import inputs  # noqa: E402
+
+METRIC = "fmm_source_period_sweeps_per_sec"
+
+
+def build_problem(cfg: int):
+    if cfg == 3:
+        return inputs.config(3)
+    if cfg == 2:
+        return inputs.config(2)
+    if cfg == 0:  # tiny smoke configuration (not a benchmark)
+        return inputs.synthetic_problem(19, 2, 24, ("Rc", "Rg", "Lc", "Lg"), nrecv=8, name="mini_129sq")
+    raise SystemExit("--config must be 2 or 3")
+
+
+def type_blocks(pb):
+    """Gather ranges of the data types present, in the reference's block order."""
+    cum = np.concatenate([[0], np.cumsum(pb.nsrc1)]).astype(int)
+    ks = [0, pb.kmaxRc, pb.kmaxRc + pb.kmaxRg, pb.kmaxRc + pb.kmaxRg + pb.kmaxLc, pb.kmax]
+    names = ["Rc", "Rg", "Lc", "Lg"]
+    return [(names[t], int(cum[ks[t]]), int(cum[ks[t + 1]])) for t in range(4) if ks[t + 1] > ks[t]]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def lsmr_bytes(nnz, m, n):
+    return 16 * nnz + 8 * (m + 1) + 12 * m + 80 * n
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, step, nthreads):
+    """Oracle sweep stage on `per_block` gathers of every data-type block; returns (sweeps, s)."""
+    import oracle_lib as O
+
+    nsw, t = 0, 0.0
+    for name, g0, g1 in blocks:
+        lo = g0 + (step * per_block) % max(1, (g1 - g0 - per_block + 1))
+        hi = min(lo + per_block, g1)
+        nrays = 16 * (hi - lo) * 2 + 16
+        t0 = time.perf_counter()
+        r = O.calsurfg_pre(pb, pv4, sen12, lo, hi, nthreads=nthreads, mode=1, maxnar=nrays * 9000)
+        t += time.perf_counter() - t0
+        assert r["err"] == 0
+        nsw += r["nsweeps"]
+    return nsw, t
+
+
+def run_reference(args, pb, pv4, sen12, blocks):
+    """--impl reference: the C++ restatement of the reference (NOT gfortran: no Fortran compiler
+    exists in this image) on all host cores, bounded sample per step."""
+    import oracle_lib as O
+
+    O.lib()
+    cores = os.cpu_count() or 1
+    per_block = max(1, min(cores // 2, 32))
+    nsw_tot, t_tot = 0, 0.0
+    for s in range(args.warmup + args.steps):
+        nsw, t = cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, s, cores)
+        if s >= args.warmup:
+            nsw_tot += nsw
+            t_tot += t
+        if s == 0 and t * (args.warmup + args.steps) > 240:  # keep the whole run within minutes
+            per_block = max(1, per_block // 2)
+    value = nsw_tot / t_tot
+    sample = f"{per_block} gathers of each of {len(blocks)} data types per step, all {cores} host threads"
+    out = dict(metric=METRIC, value=value, unit="sweeps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1e3 * t_tot / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="f32", data="synthetic", impl="reference",
+               config=dict(workload=pb.name, note="C++ restatement of reference (g++ -O3 -fopenmp, strict IEEE), "
+                           "not gfortran; bounded sample of the same workload"),
+               cpu_baseline=dict(value=value, unit="sweeps/s", cores=cores, kind="port", sample=sample),
+               e2e=dict(value=value, unit="sweeps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+               gpu_launches=0)
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(args, pb, pv4, sen12, blocks):
+    import torch
+
+    from dsurftomo_b200 import api, dist as ddist, hostglue
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumreduce(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    plan = api.Plan(pb)
+    for t in range(4):
+        if (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)[t] > 0:
+            plan.set_dispersion(t, pv4[t], *sen12[3 * t:3 * t + 3])
+        elif t in (0, 2):
+            plan.set_dispersion(t, pv4[t], None, None, None)
+    plan.finalize_dispersion()
+    nb = len(blocks)
+
+    def block_of(step):
+        return blocks[(step * world + rank) % nb]
+
+    # ---------------- timed region 1: device-resident sweep stage (CUDA events on the launching stream)
+    sampler = ClockSampler(local)
+    dev_ms, eik_ms, nsw_local, launches, wall = 0.0, 0.0, 0, 0, 0.0
+    stage = dict(eikonal_ms=0.0, rays_ms=0.0, assembly_ms=0.0)
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup:
+            barrier()
+            if rank == 0:
+                sampler.start()
+            w0 = time.perf_counter()
+        _, g0, g1 = block_of(s)
+        plan.reset_rows()
+        plan.sweeps(g0, g1)
+        if s >= args.warmup:
+            tm = plan.timings()
+            dev_ms += tm["total_ms"]
+            eik_ms += tm["eikonal_ms"]
+            nsw_local += tm["sweeps"]
+            launches += tm["launches"]
+            for k in stage:
+                stage[k] += tm[k]
+    barrier()
+    wall = time.perf_counter() - w0
+    clocks = sampler.stop() if rank == 0 else None
+    t_max_ms = maxreduce(dev_ms)
+    nsw_total = sumreduce(nsw_local)
+    value = nsw_total / (t_max_ms / 1e3)
+    Nc = ((pb.nx - 3) * 8 + 1) * ((pb.ny - 3) * 8 + 1)
+    b_sweep = 8 * (Nc + 129 * 129)  # veln read + ttn write, coarse + refined
+    peak, peak_src = peaks()
+    achieved = b_sweep * nsw_local / (eik_ms / 1e3) / 1e9
+    roofline = dict(bound="hbm", kernel="k_eikonal (+ node-state fill)", achieved=achieved, peak=peak, unit="GB/s",
+                    frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_sweep=b_sweep, launches=int(args.steps),
+                    note="latency/dependency-bound exact-order FMM replay; see DESIGN.md")
+
+    # ---------------- timed region 2: end to end through the host-buffer API (H2D + compute + D2H)
+    last = plan.download()  # sizes the pinned output buffers from the last timed step
+    cap = int(last["nar"] * 1.6) + 1024
+    pin = dict(row=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+               col=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+               rw=torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy(),
+               dsurf=torch.empty(max(pb.dall, 1), dtype=torch.float32, pin_memory=True).numpy())
+    h2d = pb.vsf.nbytes + sum(a.nbytes for a in pv4) + sum(a.nbytes for a in sen12 if a is not None) + \
+        pb.scxf.nbytes * 2 + pb.rcxf.nbytes * 2
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_t, e2e_sw, d2h = 0.0, 0, 0
+    barrier()
+    for s in range(e2e_steps):
+        _, g0, g1 = block_of(args.warmup + s)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        plan.set_model(pb.vsf)                                   # H2D: model
+        for t in range(4):                                       # H2D: this step's maps + kernels
+            if (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)[t] > 0:
+                plan.set_dispersion(t, pv4[t], *sen12[3 * t:3 * t + 3])
+            elif t in (0, 2):
+                plan.set_dispersion(t, pv4[t], None, None, None)
+        plan.finalize_dispersion()
+        plan.reset_rows()
+        plan.sweeps(g0, g1)
+        res = plan.download(out=pin)                             # D2H: predicted times + COO rows
+        torch.cuda.synchronize()
+        e2e_t += time.perf_counter() - t0
+        e2e_sw += plan.timings()["sweeps"]
+        d2h = 12 * res["nar"] + 4 * pb.dall
+    e2e_tmax = maxreduce(e2e_t)
+    e2e_value = sumreduce(e2e_sw) / e2e_tmax
+
+    # ---------------- LSMR on the rows of the last block (device-resident, then host-buffer call)
+    lsmr = None
+    if args.lsmr_iters > 0:
+        res = plan.download(out=pin)
+        r0 = int(res["row"].min()) - 1 if res["nar"] else 0
+        sub = type("P", (), {})()
+        nrows = int(res["row"].max()) - r0 if res["nar"] else 0
+        rows = (res["row"] - r0).astype(np.int32)
+        obst = pb.obst[r0:r0 + nrows]
+        cb = (obst - res["dsurf"][r0:r0 + nrows]).astype(np.float32)
+        srow, scol, sval, cnt3 = hostglue.smoothing_rows(pb.nx, pb.ny, pb.nz, nrows, pb.weight)
+        if world > 1:  # smoothing rows are shared out round-robin
+            keep = ((srow - nrows - 1) % world) == rank
+            srow, scol, sval = srow[keep], scol[keep], sval[keep]
+            _, srow = np.unique(srow, return_inverse=True)
+            srow = (srow + nrows + 1).astype(np.int32)
+            cnt3 = int(srow.max() - nrows) if len(srow) else 0
+        R = np.concatenate([rows, srow])
+        Cc = np.concatenate([res["col"], scol])
+        V = np.concatenate([res["rw"], sval])
+        b = np.concatenate([cb, np.zeros(cnt3, np.float32)])
+        m, n = nrows + cnt3, pb.maxvp
+        t0 = time.perf_counter()
+        sysl = api.LsmrSystem(m, n, R, Cc, V, b)
+        t_build = time.perf_counter() - t0
+        comm = None
+        if world > 1:
+            comm = ddist.NcclComm(rank, world, local)
+            ddist.attach(sysl, comm)
+        sysl.solve(pb.damp, itnlim=3, force_iters=True, want_x=False)  # warm-up
+        barrier()
+        L = sysl.solve(pb.damp, itnlim=args.lsmr_iters, force_iters=True, want_x=False)
+        barrier()
+        t_it = maxreduce(L["ms_total"]) / 1e3
+        nnz_tot, m_tot = sumreduce(float(sysl.nnz)), sumreduce(float(m))
+        it_s = L["itn"] / t_it
+        ach = lsmr_bytes(sysl.nnz, m, n) * L["itn"] / (L["ms_total"] / 1e3) / 1e9
+        ach_spmv = 8.0 * sysl.nnz * L["itn"] / (L["ms_spmv"] / 1e3) / 1e9
+        ach_spmtv = 8.0 * sysl.nnz * L["itn"] / (L["ms_spmtv"] / 1e3) / 1e9
+        # host-buffer LSMR call (H2D of the COO, CSR/CSC build, iterations, D2H of x)
+        t0 = time.perf_counter()
+        x = None
+        if world == 1:
+            iw = hostglue.pack_iw(R, Cc)
+            Lh = api.LSMR(m, n, len(iw), len(V), iw, V, b, pb.damp, 1e-6, 1e-6, 100.0, 400, 10)
+            t_host = time.perf_counter() - t0
+            host = dict(iters=Lh["itn"], istop=Lh["istop"], seconds=t_host, iters_per_s=Lh["itn"] / t_host,
+                        h2d_bytes=12 * len(V) + 4 * m, d2h_bytes=4 * n)
+        else:
+            host = None
+        lsmr = dict(iters_per_s=it_s, iters=L["itn"], nnz=int(nnz_tot), m=int(m_tot), n=n, build_s=t_build,
+                    roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                                  spmv_gbs=ach_spmv, spmtv_gbs=ach_spmtv, traffic=None,
+                                  algorithmic_bytes_per_iter=lsmr_bytes(sysl.nnz, m, n)),
+                    launches_per_iter=28, host_buffer_call=host)
+        sysl.close()
+        if comm:
+            comm.close()
+
+    # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        import oracle_lib as O
+
+        cores = os.cpu_count() or 1
+        per_block = max(1, min(cores // 2, 32))
+        nsw, t = cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, 0, cores)
+        cpu = dict(value=nsw / t, unit="sweeps/s", cores=cores, kind="port",
+                   sample=f"{per_block} gathers of each of {len(blocks)} data types ({nsw} sweeps, {t:.1f} s), "
+                          "C++ restatement of the reference, g++ -O3 -fopenmp strict IEEE (no Fortran compiler here)")
+        if lsmr is not None and lsmr["nnz"] <= 3e8:
+            iw = hostglue.pack_iw(R, Cc)
+            t0 = time.perf_counter()
+            Lc = O.lsmr(m, n, iw, V, b, pb.damp, itnlim=3)
+            tl = time.perf_counter() - t0
+            cpu["lsmr_iters_per_s"] = Lc["itn"] / tl
+            cpu["lsmr_sample"] = f"{Lc['itn']} iterations of the same system, 1 thread (the reference's LSMR is serial)"
+
+    if rank == 0:
+        out = dict(metric=METRIC, value=value, unit="sweeps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=t_max_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype="f32", data="synthetic",
+                   config=dict(workload=pb.name, grid=f"{(pb.nx - 3) * 8 + 1}x{(pb.ny - 3) * 8 + 1}",
+                               step="all periods x sources of one data type per rank per step "
+                                    f"({[b[0] for b in blocks]} in rotation)",
+                               receivers_per_gather=int(pb.nrc1.max()), parallelism=f"gathers sharded over {world} GPU(s)",
+                               l2="per-step working set (node states of thousands of sweeps, GBs) >> 126 MB L2",
+                               interpretation="A: quoted grid = FMM propagation grid (SURVEY.md section 8)"),
+                   roofline=roofline, cpu_baseline=cpu,
+                   e2e=dict(value=e2e_value, unit="sweeps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                            steps=e2e_steps, api="Plan.set_model/set_dispersion/sweeps/download through the C ABI "
+                                                 "with host buffers (pinned outputs)"),
+                   gpu_launches=int(launches), clocks=clocks,
+                   stage_ms_per_step={k: v / args.steps for k, v in stage.items()}, wall_s_timed=wall,
+                   lsmr=lsmr, impl="b200")
+        print(json.dumps(out))
+    plan.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--lsmr-iters", type=int, default=30)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    pb = build_problem(args.config)
+    pv4, sen12 = inputs.synthetic_dispersion(pb)
+    blocks = type_blocks(pb)
+    if args.impl == "reference":
+        run_reference(args, pb, pv4, sen12, blocks)
+    else:
+        run_b200(args, pb, pv4, sen12, blocks)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

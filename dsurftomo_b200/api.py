@@ -203,6 +203,15 @@ class Plan:
     def dispersion(self):
         check(lib().dsurf_plan_dispersion(self.h), "plan_dispersion")
 
+    def set_dispersion(self, type_, pv, sen_vs, sen_vp, sen_rho):
+        """Caller-provided dispersion results of one data type (0 Rc, 1 Rg, 2 Lc, 3 Lg)."""
+        arrs = [_c(a, F64) for a in (pv, sen_vs, sen_vp, sen_rho)]
+        check(lib().dsurf_plan_set_dispersion(self.h, C.c_int(type_), *[ptr(a, C.c_double) for a in arrs]),
+              "plan_set_dispersion")
+
+    def finalize_dispersion(self):
+        check(lib().dsurf_plan_finalize_dispersion(self.h), "plan_finalize_dispersion")
+
     def set_map(self, type_, period0, pv):
         pv = _c(pv, F64)
         check(lib().dsurf_plan_set_map(self.h, C.c_int(type_), C.c_int(period0), ptr(pv, C.c_double)), "plan_set_map")
@@ -217,12 +226,16 @@ class Plan:
     def nar(self):
         return int(lib().dsurf_plan_nar(self.h))
 
-    def download(self):
+    def download(self, out=None):
+        """Device -> host copy of everything produced so far.  `out` may hold preallocated
+        (e.g. pinned) numpy buffers 'row', 'rw', 'col', 'dsurf' of sufficient size."""
         n = self.nar
-        rows = np.zeros(max(n, 1), I32)
-        rw = np.zeros(max(n, 1), F32)
-        col = np.zeros(max(n, 1), I32)
-        dsurf = np.zeros(max(self.pb.dall, 1), F32)
+        out = out or {}
+        rows = out.get("row") if out.get("row") is not None else np.zeros(max(n, 1), I32)
+        rw = out.get("rw") if out.get("rw") is not None else np.zeros(max(n, 1), F32)
+        col = out.get("col") if out.get("col") is not None else np.zeros(max(n, 1), I32)
+        dsurf = out.get("dsurf") if out.get("dsurf") is not None else np.zeros(max(self.pb.dall, 1), F32)
+        assert len(rows) >= n and len(rw) >= n and len(col) >= n and len(dsurf) >= self.pb.dall
         rb = C.c_int(0)
         check(lib().dsurf_plan_download(self.h, ptr(rows, C.c_int), ptr(rw, C.c_float), ptr(col, C.c_int),
                                         ptr(dsurf, C.c_float), C.byref(rb)), "plan_download")
@@ -232,7 +245,8 @@ class Plan:
         ms = np.zeros(8, F64)
         check(lib().dsurf_plan_timings(self.h, ptr(ms, C.c_double)), "plan_timings")
         return dict(dispersion_ms=ms[0], dice_ms=ms[1], eikonal_ms=ms[2], rays_ms=ms[3], assembly_ms=ms[4],
-                    eikonal_launches=int(ms[5]), launches=int(ms[6]), sweeps=int(ms[7]))
+                    eikonal_launches=int(ms[5]), launches=int(ms[6]), sweeps=int(ms[7]),
+                    total_ms=float(lib().dsurf_plan_last_sweeps_ms(self.h)))
 
     def get_dispersion(self, type_):
         pb = self.pb

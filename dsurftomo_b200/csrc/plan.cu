@@ -95,6 +95,8 @@ struct dsurf_plan {
   long long nar = 0;
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evt0 = nullptr, evt1 = nullptr;
+  double ms_sweeps_total = 0;
 };
 
 static const float kPi = 3.1415926535898f;  // CalSurfG.f90:196
@@ -292,6 +294,8 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
     return DSURF_ERR_CUDA;
   }
   for (auto &e : p->ev) cudaEventCreate(&e);
+  cudaEventCreate(&p->evt0);
+  cudaEventCreate(&p->evt1);
   // ---- batch workspace sizing
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
@@ -404,6 +408,35 @@ extern "C" int dsurf_plan_dispersion(dsurf_plan *p) {
   p->ms[0] = ms;
   cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]);
   p->ms[1] = ms;
+  p->disp_done = true;
+  return DSURF_OK;
+}
+
+// Caller-provided dispersion results for one data type (same layouts as dsurf_depthkernel):
+// pv[pvcols][ncol], sen_*[nz][kmax_t][ncol].  Followed by dsurf_plan_finalize_dispersion().
+extern "C" int dsurf_plan_set_dispersion(dsurf_plan *p, int type, const double *pv, const double *sen_vs,
+                                         const double *sen_vp, const double *sen_rho) {
+  if (!p || type < 0 || type > 3) return DSURF_ERR_BAD_ARG;
+  const size_t ncol = (size_t)p->g.nx * p->g.ny;
+  if (pv) DS_CUDA(cudaMemcpy(p->pv[type].p, pv, ncol * p->pvcols[type] * sizeof(double), cudaMemcpyHostToDevice));
+  const size_t ns = ncol * p->kmaxT[type] * p->nz;
+  const double *src[3] = {sen_vs, sen_vp, sen_rho};
+  for (int q = 0; q < 3; q++)
+    if (src[q] && ns > 0) DS_CUDA(cudaMemcpy(p->sen[type][q].p, src[q], ns * sizeof(double), cudaMemcpyHostToDevice));
+  p->maps_diced = false;
+  return DSURF_OK;
+}
+extern "C" int dsurf_plan_finalize_dispersion(dsurf_plan *p) {
+  if (!p) return DSURF_ERR_BAD_ARG;
+  const Geom &g = p->g;
+  const int brocher = p->depz[p->nz - 2] < 35.0f ? 1 : 0;
+  DS_CHECK(launch_coef(p->st, p->vels.p, g.nx, g.ny, p->nz, brocher, p->coe_a.p, p->coe_rho.p));
+  for (int t = 0; t < 4; t++)
+    if (p->kmaxT[t] > 0)
+      DS_CHECK(launch_combine(p->st, p->sen[t][0].p, p->sen[t][1].p, p->sen[t][2].p, p->coe_a.p, p->coe_rho.p,
+                              g.nx * g.ny, p->kmaxT[t], p->nz - 1, p->S[t].p));
+  DS_CHECK(dice_maps(p));
+  DS_CUDA(cudaStreamSynchronize(p->st));
   p->disp_done = true;
   return DSURF_OK;
 }
@@ -558,6 +591,7 @@ extern "C" int dsurf_plan_sweeps(dsurf_plan *p, int g0, int g1) {
   g1 = std::min(g1, (int)p->gathers.size());
   for (int i = 2; i < 8; i++) p->ms[i] = 0;
   int launches = 0, nsolved = 0;
+  cudaEventRecord(p->evt0, p->st);
   std::vector<SweepDesc> hsw;
   std::vector<RayDesc> hrays;
   std::vector<float> hristr;
@@ -581,8 +615,15 @@ extern "C" int dsurf_plan_sweeps(dsurf_plan *p, int g0, int g1) {
     DS_CHECK(run_batch(p, hsw, hrays, hristr, hrayS, hrayrow, true, &launches));
     nsolved += (int)hsw.size();
   }
+  cudaEventRecord(p->evt1, p->st);
   int hflags[4];
   DS_CUDA(cudaMemcpy(hflags, p->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  {
+    float t = 0;
+    cudaEventSynchronize(p->evt1);
+    cudaEventElapsedTime(&t, p->evt0, p->evt1);
+    p->ms_sweeps_total = t;
+  }
   p->ms[6] = launches;
   p->ms[7] = nsolved;
   if (hflags[0] != 0) return hflags[0];
@@ -604,6 +645,8 @@ extern "C" int dsurf_plan_download(dsurf_plan *p, int *iw_rows, float *rw, int *
   }
   return DSURF_OK;
 }
+
+extern "C" double dsurf_plan_last_sweeps_ms(const dsurf_plan *p) { return p ? p->ms_sweeps_total : 0.0; }
 
 extern "C" int dsurf_plan_timings(const dsurf_plan *p, double *ms8) {
   if (!p || !ms8) return DSURF_ERR_BAD_ARG;

@@ -345,3 +345,38 @@ def config(n: int) -> Problem:
     if n == 5:
         return synthetic_problem(259, 32, 1024, ("Rc",), name="cfg5_2049sq_32p_1024s_Rc")
     raise ValueError(n)
+
+
+def synthetic_dispersion(pb: Problem, seed: int = 7):
+    """Deterministic synthetic dispersion results with the shapes CalSurfG's K1 stage produces,
+    for benchmarks that time the sweep stage alone (both bench arms consume exactly these arrays):
+    pv4   = [pvRc[kmax, ncol], pvRg[kmaxRg, ncol], pvLc[kmax, ncol], pvLg[kmaxLg, ncol]]
+    sen12 = 12 arrays [nz, kmax_t, ncol] ordered Rc(vs, vp, rho), Rg(...), Lc(...), Lg(...).
+    Velocities grow with period and vary smoothly (+-12 %) laterally; kernels are smooth,
+    depth-localised bumps of realistic magnitude (dc/dVs ~ 0.1-0.5, dc/dVp, dc/drho ~ +-0.05)."""
+    ncol = pb.nx * pb.ny
+    ii = np.arange(pb.nx)[None, :]
+    jj = np.arange(pb.ny)[:, None]
+    lat = (np.sin(0.21 * ii + 0.3) * np.cos(0.17 * jj) + 0.5 * np.sin(0.05 * ii * jj / max(pb.nx, 1) + seed)).ravel()
+    depth = np.asarray(pb.depz, np.float64)
+    kk = (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)
+    tt = (pb.tRc, pb.tRg, pb.tLc, pb.tLg)
+    base = (0.0, -0.08, 0.10, 0.02)
+    pv4, sen12 = [], []
+    for t in range(4):
+        cols = pb.kmax if t in (0, 2) else max(kk[t], 1)
+        pv = np.zeros((cols, ncol), np.float64)
+        for c in range(cols):
+            per = tt[t][c] if c < kk[t] else (0.5 + 0.2 * (c % max(1, max(kk))))
+            pv[c] = np.float32(0.85 + 0.12 * per + base[t]) * (1.0 + 0.12 * lat * (0.6 + 0.4 * np.cos(0.9 * c)))
+        pv4.append(pv.astype(np.float32).astype(np.float64))  # values are REAL*4-representable
+        if kk[t] == 0:
+            sen12 += [None, None, None]
+            continue
+        zc = 0.25 * np.asarray(tt[t], np.float64)[None, :, None] + 0.1  # sensitivity deepens with period
+        bump = np.exp(-(((depth[:, None, None] - zc) / (0.35 + 0.2 * zc)) ** 2))
+        mod = (1.0 + 0.2 * lat)[None, None, :]
+        sen12.append(0.45 * bump * mod)
+        sen12.append(0.05 * bump * (1.0 - 0.3 * lat)[None, None, :])
+        sen12.append(-0.04 * bump * mod + 0.01)
+    return pv4, sen12

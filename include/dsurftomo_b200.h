@@ -140,6 +140,11 @@ int dsurf_plan_destroy(dsurf_plan *plan);
 int dsurf_plan_set_model(dsurf_plan *plan, const float *vels);
 /* K1: dispersion maps + depth kernels for every data type (CalSurfG.f90:1098-1133) */
 int dsurf_plan_dispersion(dsurf_plan *plan);
+/* caller-provided dispersion results of one data type instead of K1 (layouts of dsurf_depthkernel;
+ * pv has kmax columns for Rc/Lc, kmaxRg/kmaxLg for Rg/Lg), then finalize (combine + dice) */
+int dsurf_plan_set_dispersion(dsurf_plan *plan, int type, const double *pv, const double *sen_vs,
+                              const double *sen_vp, const double *sen_rho);
+int dsurf_plan_finalize_dispersion(dsurf_plan *plan);
 /* test hook: overwrite the velocity map (nx*ny doubles) of period-type slot `map` */
 int dsurf_plan_set_map(dsurf_plan *plan, int type /*0 Rc,1 Rg,2 Lc,3 Lg*/, int period0, const double *pv);
 /* K2-K6 for gathers [g0, g1) of the flattened (knumi, srcnum) loop nest; results are appended
@@ -164,6 +169,8 @@ int dsurf_plan_get_dispersion(dsurf_plan *plan, int type, double *pv, double *se
  * [4] row assembly, [5] eikonal launches, [6] total kernel launches of last sweeps call,
  * [7] sweeps solved in the last call */
 int dsurf_plan_timings(const dsurf_plan *plan, double *ms8);
+/* device time (ms, CUDA events on the launching stream) of the whole last dsurf_plan_sweeps call */
+double dsurf_plan_last_sweeps_ms(const dsurf_plan *plan);
 
 /* Device-resident LSMR: build from host COO once, then run iterations with everything in HBM. */
 typedef struct dsurf_lsmr_sys dsurf_lsmr_sys;

@@ -166,6 +166,37 @@ def calsurfg(pb, vels=None, nthreads=1, mode=0, maxnar=None):
                 nrays=int(st[5]))
 
 
+def calsurfg_pre(pb, pv4, sen12, g_lo=-1, g_hi=-1, vels=None, nthreads=1, mode=1, maxnar=None):
+    """Gather loop of CalSurfG on caller-provided dispersion results (bench CPU arm).
+    pv4: 4 arrays [cols, ncol] (Rc, Rg, Lc, Lg); sen12: 12 arrays [nz, kmax_t, ncol] in the order
+    Rc(vs,vp,rho), Rg(...), Lc(...), Lg(...).  Entries of absent types may be None."""
+    vels = np.ascontiguousarray(pb.vsf if vels is None else vels, np.float32)
+    if maxnar is None:
+        maxnar = max(pb.maxnar(), 1)
+    iw = np.zeros(2 * maxnar + 1, np.int32)
+    rw = np.zeros(maxnar, np.float32)
+    col = np.zeros(maxnar, np.int32)
+    dsurf = np.zeros(pb.dall, np.float32)
+    nar, rbint = C.c_int(0), C.c_int(0)
+    st = np.zeros(8, np.float64)
+    dummy = np.zeros(1, np.float64)
+    keep = [np.ascontiguousarray(a if a is not None else dummy, np.float64) for a in list(pv4) + list(sen12)]
+    pvp = (C.POINTER(C.c_double) * 4)(*[_p(a, C.c_double) for a in keep[:4]])
+    senp = (C.POINTER(C.c_double) * 12)(*[_p(a, C.c_double) for a in keep[4:]])
+    err = lib().oracle_calsurfg_pre(
+        C.c_int(pb.nx), C.c_int(pb.ny), C.c_int(pb.nz), _p(vels, C.c_float), _p(iw, C.c_int), _p(rw, C.c_float),
+        _p(col, C.c_int), _p(dsurf, C.c_float), C.c_float(pb.goxd), C.c_float(pb.gozd), C.c_float(pb.dvxd),
+        C.c_float(pb.dvzd), C.c_int(pb.kmaxRc), C.c_int(pb.kmaxRg), C.c_int(pb.kmaxLc), C.c_int(pb.kmaxLg),
+        pvp, senp, _p(pb.wavetype, C.c_int), _p(pb.igrt, C.c_int), _p(pb.periods, C.c_int),
+        _p(pb.depz, C.c_float), _p(pb.scxf, C.c_float), _p(pb.sczf, C.c_float), _p(pb.rcxf, C.c_float),
+        _p(pb.rczf, C.c_float), _p(pb.nrc1, C.c_int), _p(pb.nsrc1, C.c_int), C.c_int(pb.kmax), C.c_int(pb.nsrc),
+        C.c_int(pb.nrc), C.byref(nar), C.c_int(nthreads), C.c_int(mode), C.byref(rbint), _p(st, C.c_double),
+        C.c_int(g_lo), C.c_int(g_hi))
+    n = nar.value
+    return dict(err=err, nar=n, dsurf=dsurf, rw=rw[:n].copy(), row=iw[1:n + 1].copy(), col=col[:n].copy(),
+                rbint=rbint.value, t_gather=st[1], t_fmm=st[2], t_ray=st[3], nsweeps=int(st[4]), nrays=int(st[5]))
+
+
 def pack_iw(row, col):
     """iw = [nar | rows | cols] as main.f90:463-466."""
     nar = len(row)
