@@ -346,24 +346,379 @@ __device__ int march(const Grid &G, const Heap &H, int ntr, int hcap, int lane, 
   return ntr;
 }
 
+
+// =============================================================================================
+// v2 march: same pop order and arithmetic as march<> above, restructured so that the dependent
+// memory round trips of one acceptance overlap:
+//   (1) the stencil loads of the four neighbours are issued BEFORE the root is popped (they only
+//       depend on the root's coordinates; the pop changes heap positions, never times or the
+//       alive/close/far category);
+//   (2) heap entries are single 8-byte (key,node) words; when the sift-down leaves the
+//       shared-memory levels, the next four levels below the current slot (2+4+8+16 entries) are
+//       fetched by 30 lanes in ONE round trip and the walk continues on registers via shuffles;
+//   (3) the ancestors of the (up to four) insert/update positions are fetched by 8 lanes each in
+//       one round trip; a three-entry write log keeps earlier inserts of the same acceptance
+//       coherent, and any sift that actually moves entries drops the rest of the acceptance to
+//       plain loads (rare: new trial times are almost always larger than their parents');
+//   (4) the moving element of the next pop (the last heap entry) is kept in registers whenever it
+//       is known (it is the entry appended last), or fetched together with (3).
+// Heap positions of neighbours moved by the pop itself are tracked in registers, so no status
+// re-read is needed.  Results are bit-identical to march<> (tests/test_gpu_parity.py runs both).
+// =============================================================================================
+template <int HS>
+struct Heap2 {
+  int2 *sm;  // entries [1, HS)
+  int2 *gm;  // entries [HS, hcap], indexed by absolute position
+  __device__ __forceinline__ int2 get(int p) const { return p < HS ? sm[p] : gm[p]; }
+  __device__ __forceinline__ void set(int p, int2 e) const {
+    if (p < HS)
+      sm[p] = e;
+    else
+      gm[p] = e;
+  }
+};
+__device__ __forceinline__ float keyf(int2 e) { return __int_as_float(e.x); }
+
+template <bool REFINED, int HS>
+__device__ int march2(const Grid &G, const Heap2<HS> &H, int ntr, int hcap, int lane, int vnl, int vnr, int vnt,
+                      int vnb) {
+  const int nnx = G.nnx, nnz = G.nnz;
+  const int grp = lane >> 3, q = lane & 7;
+  int2 lastE = make_int2(0, 0);
+  bool lastOK = false;
+  while (ntr > 0) {
+    const int root = H.sm[1].y;
+    const int ix = root / nnz + 1, iz = root - (ix - 1) * nnz + 1;
+    if (REFINED) {
+      int swrg = 0;
+      if (ix == 1 && vnl != 1) swrg = 1;
+      if (ix == nnx && vnr != nnx) swrg = 1;  // sic: compared with the REFINED nnx (:399-401)
+      if (iz == 1 && vnt != 1) swrg = 1;
+      if (iz == nnz && vnb != nnz) swrg = 1;
+      if (swrg) {
+        G.node[root].y = 0;
+        break;
+      }
+    }
+    G.node[root].y = 0;
+    // ---- (1) stencil loads, issued before the pop
+    int xx = ix, xz = iz;
+    if (grp == 0) xx = ix - 1;
+    if (grp == 1) xx = ix + 1;
+    if (grp == 2) xz = iz - 1;
+    if (grp == 3) xz = iz + 1;
+    const bool xin = (xx >= 1 && xx <= nnx && xz >= 1 && xz <= nnz);
+    const int xidx = xin ? (xx - 1) * nnz + (xz - 1) : -1;
+    int sx = xx, sz = xz;
+    {
+      const int off = (q & 1) ? 2 : 1;
+      const int sgn = (q & 2) ? 1 : -1;
+      if (q < 4)
+        sx = xx + sgn * off;
+      else
+        sz = xz + sgn * off;
+    }
+    const bool sin_ = xin && (sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz);
+    int2 sn = make_int2(0, kOut);
+    if (sin_) sn = G.node[(sx - 1) * nnz + (sz - 1)];
+    int2 xn = make_int2(0, 0);
+    float velx = 1.0f, risti = 0.0f;
+    if (xin) {
+      xn = G.node[xidx];
+      velx = G.vel[xidx];
+      risti = G.risti[xx - 1];
+    }
+    // ids of the four neighbours, known to every lane (for tracking heap moves)
+    const int xid0 = (ix - 1 >= 1) ? (ix - 2) * nnz + (iz - 1) : -1;
+    const int xid1 = (ix + 1 <= nnx) ? ix * nnz + (iz - 1) : -1;
+    const int xid2 = (iz - 1 >= 1) ? (ix - 1) * nnz + (iz - 2) : -1;
+    const int xid3 = (iz + 1 <= nnz) ? (ix - 1) * nnz + iz : -1;
+    int xm0 = -1, xm1 = -1, xm2 = -1, xm3 = -1;  // new positions of neighbours moved by the pop
+#define TRACK_MOVE(nid, newpos)      \
+  {                                  \
+    if ((nid) == xid0) xm0 = (newpos); \
+    if ((nid) == xid1) xm1 = (newpos); \
+    if ((nid) == xid2) xm2 = (newpos); \
+    if ((nid) == xid3) xm3 = (newpos); \
+  }
+    // ---- (2) downtree (:816-885)
+    if (ntr == 1) {
+      ntr = 0;
+      lastOK = false;
+    } else {
+      const int2 m = lastOK ? lastE : H.get(ntr);
+      const float mk = keyf(m);
+      ntr = ntr - 1;
+      int tpp = 1, tpc = 2;
+      bool stop = false;
+      while (!stop && tpc < ntr && tpc + 1 < HS) {  // both children in shared memory
+        const int2 e1 = H.sm[tpc], e2 = H.sm[tpc + 1];
+        int2 ec = e1;
+        if (keyf(e1) > keyf(e2)) {
+          tpc = tpc + 1;
+          ec = e2;
+        }
+        if (keyf(ec) < mk) {
+          H.sm[tpp] = ec;
+          G.node[ec.y].y = tpp;
+          TRACK_MOVE(ec.y, tpp);
+          tpp = tpc;
+          tpc = 2 * tpp;
+        } else {
+          stop = true;
+        }
+      }
+      while (!stop && tpc <= ntr) {
+        if (tpc + 1 < HS) {  // single child inside shared memory (tpc == ntr)
+          const int2 e1 = H.sm[tpc];
+          if (keyf(e1) < mk) {
+            H.sm[tpp] = e1;
+            G.node[e1.y].y = tpp;
+            TRACK_MOVE(e1.y, tpp);
+            tpp = tpc;
+          }
+          stop = true;
+          break;
+        }
+        // fetch the four levels below tpp: level r (1..4), offset o -> lane (2^r - 2) + o
+        const int r = (lane < 2) ? 1 : (lane < 6) ? 2 : (lane < 14) ? 3 : (lane < 30) ? 4 : 0;
+        const int o = lane - ((1 << r) - 2);
+        const long long pos = ((long long)tpp << r) + o;
+        int2 e = make_int2(0x7f800000, -1);
+        if (r > 0 && pos <= ntr) e = H.get((int)pos);
+        const int base = tpp;
+        int rel = 0;
+        for (int lvl = 1; lvl <= 4; lvl++) {
+          const long long c0 = ((long long)base << lvl) + 2 * rel;  // left child of the current slot
+          if (c0 > ntr) {
+            stop = true;
+            break;
+          }
+          const int Lc = (1 << lvl) - 2 + 2 * rel;
+          const int k1 = __shfl_sync(kFull, e.x, Lc), n1 = __shfl_sync(kFull, e.y, Lc);
+          const int k2 = __shfl_sync(kFull, e.x, Lc + 1), n2 = __shfl_sync(kFull, e.y, Lc + 1);
+          int pick = 0;
+          if (c0 < ntr && __int_as_float(k1) > __int_as_float(k2)) pick = 1;
+          const int2 ec = pick ? make_int2(k2, n2) : make_int2(k1, n1);
+          if (keyf(ec) < mk) {
+            H.set(tpp, ec);
+            G.node[ec.y].y = tpp;
+            TRACK_MOVE(ec.y, tpp);
+            tpp = (int)c0 + pick;
+            rel = 2 * rel + pick;
+            if (c0 == ntr) {  // that was the single last child
+              stop = true;
+              break;
+            }
+          } else {
+            stop = true;
+            break;
+          }
+        }
+        tpc = 2 * tpp;
+      }
+      H.set(tpp, m);
+      G.node[m.y].y = tpp;
+      TRACK_MOVE(m.y, tpp);
+      lastOK = false;
+    }
+#undef TRACK_MOVE
+    // ---- quadrants (as in march<>)
+    const float slown = 1.0f / velx;
+    const int proc = (xin && xn.y != 0) ? (xn.y == -1 ? 1 : 2) : 0;
+    const int gb = lane & ~7;
+    const int rq = q & 3;
+    const int lj = gb + 2 * (rq >> 1), lk = gb + 4 + 2 * (rq & 1);
+    const float Tj = __int_as_float(__shfl_sync(kFull, sn.x, lj));
+    const float Tj2 = __int_as_float(__shfl_sync(kFull, sn.x, lj + 1));
+    const int Sj = __shfl_sync(kFull, sn.y, lj);
+    const int Sj2 = __shfl_sync(kFull, sn.y, lj + 1);
+    const float Tk = __int_as_float(__shfl_sync(kFull, sn.x, lk));
+    const float Tk2 = __int_as_float(__shfl_sync(kFull, sn.x, lk + 1));
+    const int Sk = __shfl_sync(kFull, sn.y, lk);
+    const int Sk2 = __shfl_sync(kFull, sn.y, lk + 1);
+    float trav = 3.0e38f;
+    if (proc && q < 4 && Sj != kOut && Sk != kOut) {
+      float tq;
+      if (quadrant(Tj, Tj2, Sj, Sj2, Tk, Tk2, Sk, Sk2, slown, G.earth, risti, G.dnx, G.dnz, tq)) trav = tq;
+    }
+    trav = fminf(trav, __shfl_xor_sync(kFull, trav, 1));
+    trav = fminf(trav, __shfl_xor_sync(kFull, trav, 2));
+    // ---- (3) planned heap positions + one-shot ancestor fetch
+    int pr[4], xi[4], ppos[4];
+    float tv[4];
+    int nfar = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      pr[g] = __shfl_sync(kFull, proc, 8 * g);
+      tv[g] = __shfl_sync(kFull, trav, 8 * g);
+      xi[g] = __shfl_sync(kFull, xidx, 8 * g);
+      const int st = __shfl_sync(kFull, xn.y, 8 * g);
+      const int xm = (g == 0) ? xm0 : (g == 1) ? xm1 : (g == 2) ? xm2 : xm3;
+      ppos[g] = 0;
+      if (pr[g] == 1) {
+        nfar++;
+        ppos[g] = ntr + nfar;
+      } else if (pr[g] == 2) {
+        ppos[g] = (xm >= 0) ? xm : st;
+      }
+    }
+    const int mypos = (grp == 0) ? ppos[0] : (grp == 1) ? ppos[1] : (grp == 2) ? ppos[2] : ppos[3];
+    const int myanc = mypos >> (q + 1);
+    int2 anc = make_int2(0, -1);
+    if (myanc >= 1) anc = H.get(myanc);
+    int2 cand = make_int2(0, -1);  // candidate "last entry" for the next pop when nothing is appended
+    if (nfar == 0 && ntr >= 1) cand = H.get(ntr);
+    // ---- apply in the reference's order: x-1, x+1, z-1, z+1 (:424-486)
+    bool slow = false;
+    int ls0 = -1, ls1 = -1, ls2 = -1, ls3 = -1;
+    int2 le0 = make_int2(0, 0), le1 = le0, le2 = le0, le3 = le0;
+    int nl = 0;
+    bool appended = false;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      if (!pr[g]) continue;
+      const int xg = xi[g];
+      const float tvg = tv[g];
+      G.node[xg].x = __float_as_int(tvg);
+      int tpc;
+      if (pr[g] == 1) {
+        ntr = ntr + 1;
+        if (ntr > hcap) return -1;
+        tpc = ntr;
+      } else {
+        tpc = slow ? G.node[xg].y : ppos[g];
+      }
+      const bool use_pref = !slow && (tpc == ppos[g]);
+      int a = 0;
+      bool moved = false;
+      int tpp = tpc >> 1;
+      while (tpp > 0) {
+        int2 pe;
+        if (use_pref && a < 8) {
+          pe.x = __shfl_sync(kFull, anc.x, 8 * g + a);
+          pe.y = __shfl_sync(kFull, anc.y, 8 * g + a);
+          if (tpp == ls0) pe = le0;
+          if (tpp == ls1) pe = le1;
+          if (tpp == ls2) pe = le2;
+        } else {
+          pe = H.get(tpp);
+        }
+        if (tvg < keyf(pe)) {
+          H.set(tpc, pe);
+          G.node[pe.y].y = tpc;
+          tpc = tpp;
+          tpp = tpc >> 1;
+          a++;
+          moved = true;
+        } else {
+          tpp = 0;
+        }
+      }
+      const int2 ne = make_int2(__float_as_int(tvg), xg);
+      H.set(tpc, ne);
+      G.node[xg].y = tpc;
+      if (moved) {
+        slow = true;
+      } else {
+        if (nl == 0) { ls0 = tpc; le0 = ne; }
+        if (nl == 1) { ls1 = tpc; le1 = ne; }
+        if (nl == 2) { ls2 = tpc; le2 = ne; }
+        if (nl == 3) { ls3 = tpc; le3 = ne; }
+        nl++;
+      }
+      if (pr[g] == 1) {
+        appended = true;
+        lastE = ne;
+        lastOK = !moved;  // the entry sits at slot ntr unless it was sifted up
+      } else if (appended && moved) {
+        // a later sift that moves entries cannot touch slot ntr (it only shifts its own ancestors)
+      }
+    }
+    // ---- (4) moving element of the next pop
+    if (!appended) {
+      if (!slow && ntr >= 1) {
+        lastE = cand;
+        if (ntr == ls0) lastE = le0;
+        if (ntr == ls1) lastE = le1;
+        if (ntr == ls2) lastE = le2;
+        if (ntr == ls3) lastE = le3;
+        lastOK = true;
+      } else {
+        lastOK = false;
+      }
+    } else if (slow) {
+      lastOK = false;  // conservative: positions may have shifted
+    }
+  }
+  return ntr;
+}
+
+// sift-up for the (few) initial inserts of a pass, on the v2 heap layout
+template <int HS>
+__device__ __forceinline__ void sift_up2(const Heap2<HS> &H, const Grid &G, int tpc, float key, int xn) {
+  int tpp = tpc >> 1;
+  while (tpp > 0) {
+    const int2 pe = H.get(tpp);
+    if (key < keyf(pe)) {
+      H.set(tpc, pe);
+      G.node[pe.y].y = tpc;
+      tpc = tpp;
+      tpp = tpc >> 1;
+    } else {
+      tpp = 0;
+    }
+  }
+  H.set(tpc, make_int2(__float_as_int(key), xn));
+  G.node[xn].y = tpc;
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_fill_nodes(int2 *node, long long n) {
   const long long tot = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) node[i] = make_int2(0, -1);
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// ---- uniform interface over the two heap layouts
+__device__ __forceinline__ void heap_init(Heap &H, float *smem, int w, const BatchView &bv, int slot) {
+  H.sk = smem + (size_t)w * 2 * kHeapSm;
+  H.sn = (int *)(H.sk + kHeapSm);
+  H.gk = bv.hkey + (size_t)slot * (bv.hcap + 1);
+  H.gn = bv.hnode + (size_t)slot * (bv.hcap + 1);
+}
+template <int HS>
+__device__ __forceinline__ void heap_init(Heap2<HS> &H, float *smem, int w, const BatchView &bv, int slot) {
+  H.sm = (int2 *)smem + (size_t)w * HS;
+  H.gm = bv.hent + (size_t)slot * (bv.hcap + 1);
+}
+__device__ __forceinline__ void heap_sift(const Heap &H, const Grid &G, int tpc, float key, int xn) {
+  sift_up(H, G, tpc, key, xn);
+}
+template <int HS>
+__device__ __forceinline__ void heap_sift(const Heap2<HS> &H, const Grid &G, int tpc, float key, int xn) {
+  sift_up2(H, G, tpc, key, xn);
+}
+template <bool REFINED>
+__device__ __forceinline__ int heap_march(const Grid &G, const Heap &H, int ntr, int hcap, int lane, int a, int b,
+                                          int c, int d) {
+  return march<REFINED>(G, H, ntr, hcap, lane, a, b, c, d);
+}
+template <bool REFINED, int HS>
+__device__ __forceinline__ int heap_march(const Grid &G, const Heap2<HS> &H, int ntr, int hcap, int lane, int a,
+                                          int b, int c, int d) {
+  return march2<REFINED, HS>(G, H, ntr, hcap, lane, a, b, c, d);
+}
+
+template <class HeapT, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
           const float *__restrict__ velv_all, const float *__restrict__ risti_c, BatchView bv) {
   extern __shared__ float smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kWarpsPerBlock + w;
   if (slot >= nsw) return;
-  Heap H;
-  H.sk = smem + (size_t)w * 2 * kHeapSm;
-  H.sn = (int *)(H.sk + kHeapSm);
-  H.gk = bv.hkey + (size_t)slot * (bv.hcap + 1);
-  H.gn = bv.hnode + (size_t)slot * (bv.hcap + 1);
+  HeapT H;
+  heap_init(H, smem, w, bv, slot);
   SweepDesc d = sw[slot];
   const size_t Nc = (size_t)g.nnx * g.nnz;
   const float *veln = veln_all + (size_t)d.map * Nc;
@@ -435,10 +790,10 @@ k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__
         const int xi = (isx - 1 + i) * nrnz + (isz - 1 + j);
         noder[xi].x = __float_as_int(t0);
         ntr = ntr + 1;
-        sift_up(H, R, ntr, t0, xi);
+        heap_sift(H, R, ntr, t0, xi);
       }
   }
-  int rc = march<true>(R, H, ntr, bv.hcap, lane, d.vnl, d.vnr, d.vnt, d.vnb);
+  int rc = heap_march<true>(R, H, ntr, bv.hcap, lane, d.vnl, d.vnr, d.vnt, d.vnb);
   if (rc < 0) {
     if (lane == 0) sw[slot].status = DSURF_ERR_HEAP;
     return;
@@ -506,28 +861,43 @@ k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__
         const float key = __shfl_sync(kFull, tt, b);
         const int xi = (d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + base + b);
         ntr = ntr + 1;
-        sift_up(H, C, ntr, key, xi);
+        heap_sift(H, C, ntr, key, xi);
       }
     }
   }
-  rc = march<false>(C, H, ntr, bv.hcap, lane, 0, 0, 0, 0);
+  rc = heap_march<false>(C, H, ntr, bv.hcap, lane, 0, 0, 0, 0);
   if (rc < 0 && lane == 0) sw[slot].status = DSURF_ERR_HEAP;
 }
+
+constexpr int kHeapSm2 = 768;  // v2: 6 KB of heap per warp -> 4 blocks (32 warps) per SM
 
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
                    const float *d_velv_all, const float *d_risti, BatchView bv, int *launches) {
   if (nsw <= 0) return DSURF_OK;
   const long long ntot = (long long)nsw * g.nnx * g.nnz;
   k_fill_nodes<<<sm_count() * 8, kWarpsPerBlock * 32, 0, st>>>(bv.node, ntot);
-  const size_t smem = (size_t)kWarpsPerBlock * 2 * kHeapSm * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    DS_CUDA(cudaFuncSetAttribute(k_eikonal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static const bool use_v1 = getenv("DSURF_EIKONAL_V1") != nullptr;  // reference variant for A/B tests
   const int grid = (nsw + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  k_eikonal<<<grid, kWarpsPerBlock * 32, smem, st>>>(g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all,
-                                                    d_velv_all, d_risti, bv);
+  if (use_v1) {
+    const size_t smem = (size_t)kWarpsPerBlock * 2 * kHeapSm * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal<Heap, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    k_eikonal<Heap, 1><<<grid, kWarpsPerBlock * 32, smem, st>>>(g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all,
+                                                                d_velv_all, d_risti, bv);
+  } else {
+    const size_t smem = (size_t)kWarpsPerBlock * kHeapSm2 * sizeof(int2);
+    static bool attr = false;
+    if (!attr) {
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal<Heap2<kHeapSm2>, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+      attr = true;
+    }
+    k_eikonal<Heap2<kHeapSm2>, 4><<<grid, kWarpsPerBlock * 32, smem, st>>>(
+        g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all, d_velv_all, d_risti, bv);
+  }
   DS_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   return DSURF_OK;

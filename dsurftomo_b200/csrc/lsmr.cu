@@ -99,8 +99,9 @@ __device__ __forceinline__ float d2norm_f(float a, float b) {  // lsmrModule.f90
   return scale * sqrtf(ra * ra + rb * rb);
 }
 
-// after u = A v - alpha u : beta = ||u||  (plus its all-reduced partner in multi-GPU runs)
-__global__ void k_beta(LsmrScalars *S, const double *partial, int np, const double *extra) {
+// after u = A v - alpha u : beta = ||u||  (plus its all-reduced partner in multi-GPU runs); also
+// advances the circular-buffer pointer of the local reorthogonalisation (lsmrModule.f90:717-724)
+__global__ void k_beta(LsmrScalars *S, const double *partial, int np, const double *extra, int localVecs) {
   if (S->stop) return;
   double s = block_reduce_partials(partial, np);
   if (threadIdx.x == 0) {
@@ -111,6 +112,16 @@ __global__ void k_beta(LsmrScalars *S, const double *partial, int np, const doub
     S->beta_pos = beta > 0.0f;
     S->inv_beta = beta > 0.0f ? 1.0f / beta : 0.0f;
     S->neg_beta = -beta;
+    if (localVecs > 0 && beta > 0.0f) {
+      if (S->localPointer < localVecs) {
+        S->localPointer = S->localPointer + 1;
+      } else {
+        S->localPointer = 1;
+        S->queueFull = 1;
+      }
+      S->enq_slot = S->localPointer - 1;
+      S->orthoLimit = S->queueFull ? localVecs : S->localPointer;
+    }
   }
 }
 
@@ -128,41 +139,31 @@ __global__ void k_scale_u_enqueue(const LsmrScalars *S, float *u, int m, const f
   }
 }
 
-// advance the circular-buffer pointer (lsmrModule.f90:717-724) -- before k_scale_u_enqueue
-__global__ void k_enqueue_ptr(LsmrScalars *S, int localVecs) {
-  if (S->stop || !S->beta_pos) return;
-  if (S->localPointer < localVecs) {
-    S->localPointer = S->localPointer + 1;
-  } else {
-    S->localPointer = 1;
-    S->queueFull = 1;
-  }
-  S->enq_slot = S->localPointer - 1;
-  S->orthoLimit = S->queueFull ? localVecs : S->localPointer;
-}
-
-// reorthogonalisation step c (lsmrModule.f90:741-746):  v -= d_{c-1} q_{c-1} (if c>0), then
-// partial dot(v, q_c) (if c < limit) or partial sum(v^2) (if c == limit).
-__global__ void k_reorth(const LsmrScalars *S, float *v, const float *localV, int n, int c,
-                         double *partial) {
+// reorthogonalisation step c (lsmrModule.f90:741-746): every block first finishes step c-1
+// (d_{c-1} = REAL*4 dot product, reduced from the previous step's partials in a fixed order),
+// then v -= d_{c-1} q_{c-1}, then partial dot(v, q_c) (c < limit) or partial sum(v^2) (c == limit).
+// Partials alternate between two buffers (pin = buffer of step c-1, pout = buffer of step c);
+// steps beyond the current limit do nothing, so the alpha partials stay in buffer (limit & 1).
+__global__ void k_reorth(const LsmrScalars *S, float *v, const float *localV, int n, int c, const double *pin,
+                         double *pout, int np) {
   __shared__ double sh[256];
+  if (S->stop || !S->beta_pos) return;
+  const int lim = S->orthoLimit;
+  if (c > lim) return;
+  float dprev = 0.0f;
+  if (c > 0) dprev = (float)block_reduce_partials(pin, np);
+  __syncthreads();
   double acc = 0.0;
-  if (!S->stop && S->beta_pos) {
-    const int lim = S->orthoLimit;
-    if (c <= lim) {
-      const float dprev = S->dot_d;
-      const float *qp = (c > 0) ? localV + (size_t)(c - 1) * n : nullptr;
-      const float *qc = (c < lim) ? localV + (size_t)c * n : nullptr;
-      const long long tot = (long long)gridDim.x * blockDim.x;
-      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) {
-        float vi = v[i];
-        if (qp) {
-          vi = vi - dprev * qp[i];
-          v[i] = vi;
-        }
-        acc += qc ? (double)vi * (double)qc[i] : (double)vi * (double)vi;
-      }
+  const float *qp = (c > 0) ? localV + (size_t)(c - 1) * n : nullptr;
+  const float *qc = (c < lim) ? localV + (size_t)c * n : nullptr;
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) {
+    float vi = v[i];
+    if (qp) {
+      vi = vi - dprev * qp[i];
+      v[i] = vi;
     }
+    acc += qc ? (double)vi * (double)qc[i] : (double)vi * (double)vi;
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -170,29 +171,23 @@ __global__ void k_reorth(const LsmrScalars *S, float *v, const float *localV, in
     if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
-}
-
-// finish step c: d_c = dot (REAL*4), or alpha = ||v|| when c == limit
-__global__ void k_reorth_fin(LsmrScalars *S, const double *partial, int np, int c) {
-  if (S->stop || !S->beta_pos) return;
-  if (c > S->orthoLimit) return;
-  const double s = block_reduce_partials(partial, np);
-  if (threadIdx.x == 0) {
-    if (c < S->orthoLimit) {
-      S->dot_d = (float)s;
-    } else {
-      const float alpha = (float)sqrt(s);
-      S->alpha = alpha;
-      S->inv_alpha = alpha > 0.0f ? 1.0f / alpha : 1.0f;
-      S->alpha_pos = alpha > 0.0f;
-    }
-  }
+  if (threadIdx.x == 0) pout[blockIdx.x] = sh[0];
 }
 
 // plane rotations + estimates up to the vector updates (lsmrModule.f90:508-537)
-__global__ void k_rotations(LsmrScalars *S, float damp) {
+__global__ void k_rotations(LsmrScalars *S, float damp, const double *part0, const double *part1, int np) {
   if (S->stop) return;
+  if (S->beta_pos) {  // alpha = ||v|| from the partials of the last reorthogonalisation step
+    const double s = block_reduce_partials((S->orthoLimit & 1) ? part1 : part0, np);
+    if (threadIdx.x == 0) {
+      const float a = (float)sqrt(s);
+      S->alpha = a;
+      S->inv_alpha = a > 0.0f ? 1.0f / a : 1.0f;
+      S->alpha_pos = a > 0.0f;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   const float alpha = S->alpha, beta = S->beta;
   const float alphahat = d2norm_f(S->alphabar, damp);
   const float chat = S->alphabar / alphahat;
@@ -517,7 +512,7 @@ struct dsurf_lsmr_sys {
   DevBuf<int> csr_col, csc_row;
   DevBuf<float> csr_val, csc_val;
   DevBuf<float> b, u, v, h, hbar, x, localV;
-  DevBuf<double> partial;
+  DevBuf<double> partial, partial2;
   DevBuf<LsmrScalars> S;
   int np_cap = 0;
   // multi-GPU (rows partitioned over ranks): see lsmr_dist in capi.cu
@@ -546,7 +541,7 @@ int lsmr_sys_create_dev(dsurf_lsmr_sys **out, int m, int n, long long nnz, const
   const int np = std::max((m + kSpmvWarps - 1) / kSpmvWarps, (n + kSpmvWarps - 1) / kSpmvWarps) + 1024;
   s->np_cap = np;
   if (s->b.reserve(m) || s->u.reserve(m) || s->v.reserve(n) || s->h.reserve(n) || s->hbar.reserve(n) ||
-      s->x.reserve(n) || s->partial.reserve(np) || s->S.reserve(1) || s->vpart.reserve(n + 8) ||
+      s->x.reserve(n) || s->partial.reserve(np) || s->partial2.reserve(np) || s->S.reserve(1) || s->vpart.reserve(n + 8) ||
       s->red.reserve(8)) {
     set_error(__FILE__, __LINE__, "cudaMalloc failed (lsmr vectors)");
     delete s;
@@ -605,6 +600,7 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   }
   LsmrScalars *S = s->S.p;
   double *part = s->partial.p;
+  double *part2 = s->partial2.p;
   const int gu = (m + kSpmvWarps - 1) / kSpmvWarps, gv = (n + kSpmvWarps - 1) / kSpmvWarps;
   const int gvec = std::min(std::max((n + 255) / 256, 1), sm_count() * 4);
   const int gvecm = std::min(std::max((std::max(m, n) + 255) / 256, 1), sm_count() * 4);
@@ -652,8 +648,7 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
                                                 &S->alpha, -1.0f, m, part, &S->stop);
     cudaEventRecord(eb, st);
     if (!dist) {
-      k_beta<<<1, 1024, 0, st>>>(S, part, gu, nullptr);
-      if (localVecs > 0) k_enqueue_ptr<<<1, 1, 0, st>>>(S, localVecs);
+      k_beta<<<1, 1024, 0, st>>>(S, part, gu, nullptr, localVecs);
       k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
       // v = A'u - beta v (:495-497)
       cudaEventRecord(ec, st);
@@ -668,18 +663,15 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
                                                   s->vpart.p, nullptr, 0.0f, n, nullptr, &S->stop);
       cudaEventRecord(ed, st);
       DS_CHECK(lsmr_allreduce(s->comm, s->vpart.p, n, s->red.p, 1, st));
-      k_beta<<<1, 1024, 0, st>>>(S, part, gu, s->red.p);
-      if (localVecs > 0) k_enqueue_ptr<<<1, 1, 0, st>>>(S, localVecs);
+      k_beta<<<1, 1024, 0, st>>>(S, part, gu, s->red.p, localVecs);
       k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
       k_combine_v<<<gvec, 256, 0, st>>>(S, s->v.p, s->vpart.p, n);
     }
     // local reorthogonalisation + alpha (:498-504, 731-748); steps beyond the current limit no-op
     const int maxsteps = localVecs;  // c = 0..limit, limit <= localVecs
-    for (int c = 0; c <= maxsteps; c++) {
-      k_reorth<<<gvec, 256, 0, st>>>(S, s->v.p, s->localV.p, n, c, part);
-      k_reorth_fin<<<1, 256, 0, st>>>(S, part, gvec, c);
-    }
-    k_rotations<<<1, 1, 0, st>>>(S, damp);
+    for (int c = 0; c <= maxsteps; c++)
+      k_reorth<<<gvec, 256, 0, st>>>(S, s->v.p, s->localV.p, n, c, (c & 1) ? part : part2, (c & 1) ? part2 : part, gvec);
+    k_rotations<<<1, 256, 0, st>>>(S, damp, part, part2, gvec);
     k_update<<<gvec, 256, 0, st>>>(S, s->v.p, s->h.p, s->hbar.p, s->x.p, n, part);
     k_tests<<<1, 1024, 0, st>>>(S, part, gvec, atol, btol, ctol, itnlim, force_iters);
     DS_CUDA(cudaMemcpyAsync(&h_stop, &S->stop, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -80,6 +80,7 @@ struct dsurf_plan {
   DevBuf<int2> node, noder;
   DevBuf<float> velr, hkey, ristr;
   DevBuf<int> hnode;
+  DevBuf<int2> hent;
   DevBuf<SweepDesc> d_sw;
   DevBuf<RayDesc> d_rays;
   DevBuf<float> fdm;
@@ -304,7 +305,7 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
   int maxnrc = 1;
   for (auto &gi : p->gathers) maxnrc = std::max(maxnrc, gi.nrc);
   const size_t per_slot = Nc * sizeof(int2) + (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) +
-                          (size_t)(p->hcap + 1) * 8 + kRefMax * sizeof(float) + sizeof(SweepDesc) +
+                          (size_t)(p->hcap + 1) * 16 + kRefMax * sizeof(float) + sizeof(SweepDesc) +
                           (size_t)maxnrc * (fdm_per_ray + sizeof(RayDesc) + 64);
   const size_t budget = std::min<size_t>((size_t)(freeb * 0.55), (size_t)64 << 30);
   long long nsw_total = 0;
@@ -321,6 +322,7 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
   bad |= p->velr.reserve((size_t)p->maxslots * kRefMax * kRefMax) != cudaSuccess;
   bad |= p->hkey.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
   bad |= p->hnode.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
+  bad |= p->hent.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
   bad |= p->ristr.reserve((size_t)p->maxslots * kRefMax) != cudaSuccess;
   bad |= p->d_sw.reserve(p->maxslots) != cudaSuccess;
   bad |= p->d_rays.reserve(p->maxrays) != cudaSuccess;
@@ -487,6 +489,7 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
     bv.velr = p->velr.p;
     bv.hkey = p->hkey.p;
     bv.hnode = p->hnode.p;
+    bv.hent = p->hent.p;
     bv.ristr = p->ristr.p;
     bv.hcap = p->hcap;
     cudaEventRecord(p->ev[0], st);
@@ -509,7 +512,8 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
       return DSURF_ERR_HEAP;
     }
     p->hcap = (int)std::min<long long>(maxbt, (long long)p->hcap * 8);
-    if (p->hkey.reserve((size_t)p->maxslots * (p->hcap + 1)) || p->hnode.reserve((size_t)p->maxslots * (p->hcap + 1))) {
+    if (p->hkey.reserve((size_t)p->maxslots * (p->hcap + 1)) || p->hnode.reserve((size_t)p->maxslots * (p->hcap + 1)) ||
+        p->hent.reserve((size_t)p->maxslots * (p->hcap + 1))) {
       set_error(__FILE__, __LINE__, "cudaMalloc failed (heap growth)");
       return DSURF_ERR_CUDA;
     }
@@ -523,6 +527,7 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
     bv.velr = p->velr.p;
     bv.hkey = p->hkey.p;
     bv.hnode = p->hnode.p;
+    bv.hent = p->hent.p;
     bv.ristr = p->ristr.p;
     bv.hcap = p->hcap;
     cudaEventRecord(p->ev[2], st);

@@ -74,6 +74,7 @@ struct BatchView {
   float *velr;       // [slot][129*129] refined velocity
   float *hkey;       // [slot][hcap+1] heap keys beyond the shared-memory part
   int *hnode;        // [slot][hcap+1]
+  int2 *hent;        // [slot][hcap+1] (key,node) entries of the v2 heap layout
   const float *ristr; // [slot][129] earth*sin(gorx+(ix-1)*drnx), host libm
   int hcap;
 };

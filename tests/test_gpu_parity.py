@@ -245,3 +245,17 @@ def test_outer_iteration_model_update(taipei):
     vs_ref, _ = O.model_update(pb, pb.vsf, L["x"])
     assert m == s["m"]
     assert np.abs(vs_new / vs_ref - 1).max() <= 1e-5
+
+
+def test_reference_eikonal_variant_also_bit_exact():
+    """The simple (v1) march and the overlapped (v2) march must both reproduce the oracle; v1 is
+    selected with DSURF_EIKONAL_V1=1 at process start."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, DSURF_EIKONAL_V1="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "sweep_bit_exact or calsurfg_small"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
