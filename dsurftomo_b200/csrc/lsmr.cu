@@ -29,31 +29,54 @@ namespace dsurf {
 // Optionally accumulates sum(y^2) per block into partial[blockIdx.x] (fixed order).
 // ---------------------------------------------------------------------------------------------
 constexpr int kSpmvWarps = 8;
+constexpr int kShortRow = 32;  // rows/columns with fewer entries are handled one per thread
 
+// Long rows: one warp per row, 16-byte vector loads of (idx,val) after peeling to a 16-byte
+// boundary, two vectors (8 entries) per lane in flight.  rowlist == nullptr -> rows 0..nrows-1.
 __global__ void __launch_bounds__(kSpmvWarps * 32)
 k_spmv_warp(const long long *__restrict__ ptr, const int *__restrict__ idx,
             const float *__restrict__ val, const float *__restrict__ x, float *__restrict__ y,
-            const float *__restrict__ scale_ptr, float scale_sign, int nrows,
-            double *__restrict__ partial, const int *__restrict__ stop) {
+            const float *__restrict__ scale_ptr, float scale_sign, const int *__restrict__ rowlist,
+            int nrows, double *__restrict__ partial, const int *__restrict__ stop) {
   __shared__ double sh[kSpmvWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int r = blockIdx.x * kSpmvWarps + w;
+  const int wi = blockIdx.x * kSpmvWarps + w;
   double sq = 0.0;
   if (stop == nullptr || *stop == 0) {
-    if (r < nrows) {
+    if (wi < nrows) {
+      const int r = rowlist ? rowlist[wi] : wi;
       const long long b = ptr[r], e = ptr[r + 1];
-      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-      long long k = b + lane;
-      for (; k + 96 < e; k += 128) {  // 4 independent 128-byte streams in flight per array
-        const int i0 = idx[k], i1 = idx[k + 32], i2 = idx[k + 64], i3 = idx[k + 96];
-        const float v0 = val[k], v1 = val[k + 32], v2 = val[k + 64], v3 = val[k + 96];
-        acc0 += (double)v0 * (double)__ldg(x + i0);
-        acc1 += (double)v1 * (double)__ldg(x + i1);
-        acc2 += (double)v2 * (double)__ldg(x + i2);
-        acc3 += (double)v3 * (double)__ldg(x + i3);
+      long long k0 = (b + 3) & ~3LL;
+      if (k0 > e) k0 = e;
+      double acc0 = 0.0, acc1 = 0.0;
+      if (b + lane < k0) acc0 += (double)val[b + lane] * (double)__ldg(x + idx[b + lane]);
+      const long long nv = (e - k0) >> 2;
+      const int4 *idx4 = reinterpret_cast<const int4 *>(idx + k0);
+      const float4 *val4 = reinterpret_cast<const float4 *>(val + k0);
+      long long v = lane;
+      for (; v + 32 < nv; v += 64) {
+        const int4 ia = idx4[v], ib = idx4[v + 32];
+        const float4 va = val4[v], vb = val4[v + 32];
+        acc0 += (double)va.x * (double)__ldg(x + ia.x);
+        acc1 += (double)va.y * (double)__ldg(x + ia.y);
+        acc0 += (double)va.z * (double)__ldg(x + ia.z);
+        acc1 += (double)va.w * (double)__ldg(x + ia.w);
+        acc0 += (double)vb.x * (double)__ldg(x + ib.x);
+        acc1 += (double)vb.y * (double)__ldg(x + ib.y);
+        acc0 += (double)vb.z * (double)__ldg(x + ib.z);
+        acc1 += (double)vb.w * (double)__ldg(x + ib.w);
       }
-      for (; k < e; k += 32) acc0 += (double)val[k] * (double)__ldg(x + idx[k]);
-      double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
+      for (; v < nv; v += 32) {
+        const int4 ia = idx4[v];
+        const float4 va = val4[v];
+        acc0 += (double)va.x * (double)__ldg(x + ia.x);
+        acc1 += (double)va.y * (double)__ldg(x + ia.y);
+        acc0 += (double)va.z * (double)__ldg(x + ia.z);
+        acc1 += (double)va.w * (double)__ldg(x + ia.w);
+      }
+      const long long kt = k0 + (nv << 2) + lane;
+      if (kt < e) acc1 += (double)val[kt] * (double)__ldg(x + idx[kt]);
+      const double acc = warp_sum(acc0 + acc1);
       if (lane == 0) {
         const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
         const float y0 = scale_ptr ? s * y[r] : 0.0f;
@@ -72,6 +95,37 @@ k_spmv_warp(const long long *__restrict__ ptr, const int *__restrict__ idx,
       for (int i = 0; i < kSpmvWarps; i++) t += sh[i];
       partial[blockIdx.x] = t;
     }
+  }
+}
+
+// Short rows (e.g. the 1- and 7-entry smoothing rows): one thread per row.
+__global__ void __launch_bounds__(256)
+k_spmv_short(const long long *__restrict__ ptr, const int *__restrict__ idx, const float *__restrict__ val,
+             const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ scale_ptr,
+             float scale_sign, const int *__restrict__ rowlist, int nrows, double *__restrict__ partial,
+             const int *__restrict__ stop) {
+  __shared__ double sh[256];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double sq = 0.0;
+  if ((stop == nullptr || *stop == 0) && t < nrows) {
+    const int r = rowlist[t];
+    const long long b = ptr[r], e = ptr[r + 1];
+    double acc = 0.0;
+    for (long long k = b; k < e; k++) acc += (double)val[k] * (double)__ldg(x + idx[k]);
+    const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
+    const float y0 = scale_ptr ? s * y[r] : 0.0f;
+    const float yn = (float)((double)y0 + acc);
+    y[r] = yn;
+    sq = (double)yn * (double)yn;
+  }
+  if (partial) {
+    sh[threadIdx.x] = sq;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
   }
 }
 
@@ -504,45 +558,100 @@ static int build_compressed(cudaStream_t st, const int *keys1, const int *other1
 
 using namespace dsurf;
 
+// one compressed structure (CSR of A, or CSC of A) with its long/short row classification
+struct Compressed {
+  DevBuf<long long> ptr;
+  DevBuf<int> idx;
+  DevBuf<float> val;
+  DevBuf<int> longl, shortl;
+  int nrows = 0, nlong = 0, nshort = 0;
+  int blocks() const { return (nlong + kSpmvWarps - 1) / kSpmvWarps + (nshort + 255) / 256; }
+};
+
 struct dsurf_lsmr_sys {
   int m = 0, n = 0;
   long long nnz = 0;
   cudaStream_t st = nullptr;
-  DevBuf<long long> row_ptr, col_ptr;
-  DevBuf<int> csr_col, csc_row;
-  DevBuf<float> csr_val, csc_val;
+  bool own_stream = false;
+  Compressed A, At;  // A: rows of A (u += A v); At: columns of A (v += A'u)
   DevBuf<float> b, u, v, h, hbar, x, localV;
   DevBuf<double> partial, partial2;
   DevBuf<LsmrScalars> S;
   int np_cap = 0;
-  // multi-GPU (rows partitioned over ranks): see lsmr_dist in capi.cu
+  // multi-GPU (rows partitioned over ranks): NCCL communicator owned by the host side (dist.cu)
   void *comm = nullptr;
   int rank = 0, nranks = 1;
   DevBuf<float> vpart;
   DevBuf<double> red;
+  ~dsurf_lsmr_sys() {
+    if (own_stream && st) cudaStreamDestroy(st);
+  }
 };
 
 namespace dsurf {
-int lsmr_allreduce(void *comm, float *buf, size_t n, double *dbuf, size_t nd, cudaStream_t st);  // capi.cu
+int lsmr_allreduce(void *comm, float *buf, size_t n, double *dbuf, size_t nd, cudaStream_t st);  // dist.cu
+
+static int classify_rows(cudaStream_t st, Compressed &C, int nrows) {
+  std::vector<long long> hp((size_t)nrows + 1);
+  DS_CUDA(cudaMemcpyAsync(hp.data(), C.ptr.p, ((size_t)nrows + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> lo, sh;
+  for (int r = 0; r < nrows; r++) {
+    const long long len = hp[r + 1] - hp[r];
+    if (len >= kShortRow)
+      lo.push_back(r);
+    else
+      sh.push_back(r);  // includes empty rows (they still need y = s*y)
+  }
+  C.nrows = nrows;
+  C.nlong = (int)lo.size();
+  C.nshort = (int)sh.size();
+  if (C.longl.reserve(std::max<size_t>(1, lo.size())) || C.shortl.reserve(std::max<size_t>(1, sh.size()))) return DSURF_ERR_CUDA;
+  if (!lo.empty()) DS_CUDA(cudaMemcpyAsync(C.longl.p, lo.data(), lo.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!sh.empty()) DS_CUDA(cudaMemcpyAsync(C.shortl.p, sh.data(), sh.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  return DSURF_OK;
+}
+
+// y = s*y + C x (all rows); partial (may be null) receives C.blocks() block sums of y^2
+static void launch_product(cudaStream_t st, const Compressed &C, const float *x, float *y, const float *scale_ptr,
+                           float sign, double *partial, const int *stop) {
+  const int ga = (C.nlong + kSpmvWarps - 1) / kSpmvWarps;
+  if (C.nlong > 0)
+    k_spmv_warp<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, C.val.p, x, y, scale_ptr, sign, C.longl.p, C.nlong,
+                                                partial, stop);
+  if (C.nshort > 0)
+    k_spmv_short<<<(C.nshort + 255) / 256, 256, 0, st>>>(C.ptr.p, C.idx.p, C.val.p, x, y, scale_ptr, sign, C.shortl.p,
+                                                         C.nshort, partial ? partial + ga : nullptr, stop);
+}
 
 int lsmr_sys_create_dev(dsurf_lsmr_sys **out, int m, int n, long long nnz, const int *d_rows1,
-                        const int *d_cols1, const float *d_vals, const float *d_b, cudaStream_t st) {
+                        const int *d_cols1, const float *d_vals, const float *d_b) {
   auto *s = new dsurf_lsmr_sys();
   s->m = m;
   s->n = n;
   s->nnz = nnz;
-  s->st = st;
-  int rc = build_compressed(st, d_rows1, d_cols1, d_vals, nnz, m, s->row_ptr, s->csr_col, s->csr_val);
-  if (rc == DSURF_OK) rc = build_compressed(st, d_cols1, d_rows1, d_vals, nnz, n, s->col_ptr, s->csc_row, s->csc_val);
+  if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error(__FILE__, __LINE__, "cudaStreamCreate failed");
+    delete s;
+    return DSURF_ERR_CUDA;
+  }
+  s->own_stream = true;
+  cudaStream_t st = s->st;
+  cudaDeviceSynchronize();  // inputs were uploaded on the legacy default stream
+  int rc = build_compressed(st, d_rows1, d_cols1, d_vals, nnz, m, s->A.ptr, s->A.idx, s->A.val);
+  if (rc == DSURF_OK) rc = build_compressed(st, d_cols1, d_rows1, d_vals, nnz, n, s->At.ptr, s->At.idx, s->At.val);
+  if (rc == DSURF_OK) rc = classify_rows(st, s->A, m);
+  if (rc == DSURF_OK) rc = classify_rows(st, s->At, n);
   if (rc != DSURF_OK) {
     delete s;
     return rc;
   }
-  const int np = std::max((m + kSpmvWarps - 1) / kSpmvWarps, (n + kSpmvWarps - 1) / kSpmvWarps) + 1024;
+  const int np = std::max(std::max(s->A.blocks(), s->At.blocks()), 4096) + 16;
   s->np_cap = np;
   if (s->b.reserve(m) || s->u.reserve(m) || s->v.reserve(n) || s->h.reserve(n) || s->hbar.reserve(n) ||
-      s->x.reserve(n) || s->partial.reserve(np) || s->partial2.reserve(np) || s->S.reserve(1) || s->vpart.reserve(n + 8) ||
-      s->red.reserve(8)) {
+      s->x.reserve(n) || s->partial.reserve(np) || s->partial2.reserve(np) || s->S.reserve(1) ||
+      s->vpart.reserve(n + 8) || s->red.reserve(8)) {
     set_error(__FILE__, __LINE__, "cudaMalloc failed (lsmr vectors)");
     delete s;
     return DSURF_ERR_CUDA;
@@ -569,7 +678,7 @@ extern "C" int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar
   DS_CUDA(cudaMemcpy(dc.p, cols1, nar * sizeof(int), cudaMemcpyHostToDevice));
   DS_CUDA(cudaMemcpy(dv.p, vals, nar * sizeof(float), cudaMemcpyHostToDevice));
   DS_CUDA(cudaMemcpy(db.p, b, (size_t)m * sizeof(float), cudaMemcpyHostToDevice));
-  return lsmr_sys_create_dev(sys, m, n, nar, dr.p, dc.p, dv.p, db.p, 0);
+  return lsmr_sys_create_dev(sys, m, n, nar, dr.p, dc.p, dv.p, db.p);
 }
 
 extern "C" int dsurf_lsmr_destroy(dsurf_lsmr_sys *sys) {
@@ -582,6 +691,40 @@ extern "C" int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *comm, int rank, in
   sys->comm = comm;
   sys->rank = rank;
   sys->nranks = nranks;
+  return DSURF_OK;
+}
+
+// one LSMR iteration's kernel sequence (lsmrModule.f90:475-616) on stream st
+static int enqueue_iteration(dsurf_lsmr_sys *s, float damp, float atol, float btol, float ctol, int itnlim,
+                             int force_iters, int localVecs, bool dist) {
+  cudaStream_t st = s->st;
+  const int m = s->m, n = s->n;
+  LsmrScalars *S = s->S.p;
+  double *part = s->partial.p, *part2 = s->partial2.p;
+  const int gvec = std::min(std::max((n + 255) / 256, 1), sm_count() * 4);
+  const int gvecm = std::min(std::max((std::max(m, n) + 255) / 256, 1), sm_count() * 4);
+  // u = A v - alpha u ; beta (:484-487)
+  launch_product(st, s->A, s->v.p, s->u.p, &S->alpha, -1.0f, part, &S->stop);
+  if (!dist) {
+    k_beta<<<1, 1024, 0, st>>>(S, part, s->A.blocks(), nullptr, localVecs);
+    k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    // v = A'u - beta v (:495-497)
+    launch_product(st, s->At, s->u.p, s->v.p, &S->neg_beta, 1.0f, nullptr, &S->stop);
+  } else {
+    // one fused exchange per iteration: partial A'u_raw (n floats) + partial ||u||^2 (1 double)
+    k_reduce_to<<<1, 1024, 0, st>>>(s->red.p, part, s->A.blocks());
+    launch_product(st, s->At, s->u.p, s->vpart.p, nullptr, 0.0f, nullptr, &S->stop);
+    DS_CHECK(lsmr_allreduce(s->comm, s->vpart.p, n, s->red.p, 1, st));
+    k_beta<<<1, 1024, 0, st>>>(S, part, s->A.blocks(), s->red.p, localVecs);
+    k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    k_combine_v<<<gvec, 256, 0, st>>>(S, s->v.p, s->vpart.p, n);
+  }
+  // local reorthogonalisation + alpha (:498-504, 731-748); steps beyond the current limit no-op
+  for (int c = 0; c <= localVecs; c++)
+    k_reorth<<<gvec, 256, 0, st>>>(S, s->v.p, s->localV.p, n, c, (c & 1) ? part : part2, (c & 1) ? part2 : part, gvec);
+  k_rotations<<<1, 256, 0, st>>>(S, damp, part, part2, gvec);
+  k_update<<<gvec, 256, 0, st>>>(S, s->v.p, s->h.p, s->hbar.p, s->x.p, n, part);
+  k_tests<<<1, 1024, 0, st>>>(S, part, gvec, atol, btol, ctol, itnlim, force_iters);
   return DSURF_OK;
 }
 
@@ -600,22 +743,19 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   }
   LsmrScalars *S = s->S.p;
   double *part = s->partial.p;
-  double *part2 = s->partial2.p;
-  const int gu = (m + kSpmvWarps - 1) / kSpmvWarps, gv = (n + kSpmvWarps - 1) / kSpmvWarps;
   const int gvec = std::min(std::max((n + 255) / 256, 1), sm_count() * 4);
   const int gvecm = std::min(std::max((std::max(m, n) + 255) / 256, 1), sm_count() * 4);
   const float ctol = conlim > 0.0f ? 1.0f / conlim : 0.0f;
-  cudaEvent_t e0, e1, ea, eb, ec, ed;
-  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&ea); cudaEventCreate(&eb);
-  cudaEventCreate(&ec); cudaEventCreate(&ed);
-  double t_spmv = 0, t_spmtv = 0;
+  const bool dist = s->comm != nullptr && s->nranks > 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
   DS_CUDA(cudaMemsetAsync(S, 0, sizeof(LsmrScalars), st));
   DS_CUDA(cudaMemsetAsync(s->x.p, 0, (size_t)n * sizeof(float), st));
   DS_CUDA(cudaMemsetAsync(s->hbar.p, 0, (size_t)n * sizeof(float), st));
   DS_CUDA(cudaMemsetAsync(s->v.p, 0, (size_t)n * sizeof(float), st));
   cudaEventRecord(e0, st);
   // ---- u = b ; beta = ||u|| ; u /= beta ; v = A'u ; alpha = ||v|| ; v /= alpha (:380-397)
-  const bool dist = s->comm != nullptr && s->nranks > 1;
   k_sumsq<<<gvecm, 256, 0, st>>>(s->b.p, m, part);
   if (dist) {
     k_reduce_to<<<1, 1024, 0, st>>>(s->red.p, part, gvecm);
@@ -624,12 +764,10 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   k_init_beta<<<1, 1024, 0, st>>>(S, part, gvecm, dist ? s->red.p : nullptr);
   k_init_scale_copy<<<gvecm, 256, 0, st>>>(s->u.p, s->b.p, nullptr, &S->inv_beta, m);
   if (!dist) {
-    k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
-                                                nullptr, 0.0f, n, part, nullptr);
-    k_init_alpha<<<1, 1024, 0, st>>>(S, part, gv, localVecs);
+    launch_product(st, s->At, s->u.p, s->v.p, nullptr, 0.0f, part, nullptr);
+    k_init_alpha<<<1, 1024, 0, st>>>(S, part, s->At.blocks(), localVecs);
   } else {
-    k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
-                                                nullptr, 0.0f, n, nullptr, nullptr);
+    launch_product(st, s->At, s->u.p, s->v.p, nullptr, 0.0f, nullptr, nullptr);
     DS_CHECK(lsmr_allreduce(s->comm, s->v.p, n, nullptr, 0, st));
     k_sumsq<<<gvec, 256, 0, st>>>(s->v.p, n, part);
     k_init_alpha<<<1, 1024, 0, st>>>(S, part, gvec, localVecs);
@@ -640,47 +778,41 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   int h_stop = 0;
   DS_CUDA(cudaMemcpyAsync(&h_stop, &S->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
   DS_CUDA(cudaStreamSynchronize(st));
-  int iters_launched = 0;
-  while (!h_stop) {
-    // u = A v - alpha u ; beta (:484-487)
-    cudaEventRecord(ea, st);
-    k_spmv_warp<<<gu, kSpmvWarps * 32, 0, st>>>(s->row_ptr.p, s->csr_col.p, s->csr_val.p, s->v.p, s->u.p,
-                                                &S->alpha, -1.0f, m, part, &S->stop);
-    cudaEventRecord(eb, st);
-    if (!dist) {
-      k_beta<<<1, 1024, 0, st>>>(S, part, gu, nullptr, localVecs);
-      k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
-      // v = A'u - beta v (:495-497)
-      cudaEventRecord(ec, st);
-      k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p, s->v.p,
-                                                  &S->neg_beta, 1.0f, n, nullptr, &S->stop);
-      cudaEventRecord(ed, st);
+  DS_CUDA(cudaGetLastError());
+  // ---- main loop.  Single GPU: the iteration is captured once into a CUDA graph and replayed;
+  // every kernel no-ops once the device-side stop flag is set, so the host only polls the flag
+  // every kPoll iterations (the solution is frozen at the exact stopping iteration).
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  const bool use_graph = !dist && getenv("DSURF_LSMR_NO_GRAPH") == nullptr;
+  if (use_graph && !h_stop) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int rc = enqueue_iteration(s, damp, atol, btol, ctol, itnlim, force_iters, localVecs, false);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc != DSURF_OK || ce != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr;
+        gexec = nullptr;
+        cudaGetLastError();
+      }
     } else {
-      // one fused exchange per iteration: partial A'u_raw (n floats) + partial ||u||^2 (1 double)
-      k_reduce_to<<<1, 1024, 0, st>>>(s->red.p, part, gu);
-      cudaEventRecord(ec, st);
-      k_spmv_warp<<<gv, kSpmvWarps * 32, 0, st>>>(s->col_ptr.p, s->csc_row.p, s->csc_val.p, s->u.p,
-                                                  s->vpart.p, nullptr, 0.0f, n, nullptr, &S->stop);
-      cudaEventRecord(ed, st);
-      DS_CHECK(lsmr_allreduce(s->comm, s->vpart.p, n, s->red.p, 1, st));
-      k_beta<<<1, 1024, 0, st>>>(S, part, gu, s->red.p, localVecs);
-      k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
-      k_combine_v<<<gvec, 256, 0, st>>>(S, s->v.p, s->vpart.p, n);
+      cudaGetLastError();
     }
-    // local reorthogonalisation + alpha (:498-504, 731-748); steps beyond the current limit no-op
-    const int maxsteps = localVecs;  // c = 0..limit, limit <= localVecs
-    for (int c = 0; c <= maxsteps; c++)
-      k_reorth<<<gvec, 256, 0, st>>>(S, s->v.p, s->localV.p, n, c, (c & 1) ? part : part2, (c & 1) ? part2 : part, gvec);
-    k_rotations<<<1, 256, 0, st>>>(S, damp, part, part2, gvec);
-    k_update<<<gvec, 256, 0, st>>>(S, s->v.p, s->h.p, s->hbar.p, s->x.p, n, part);
-    k_tests<<<1, 1024, 0, st>>>(S, part, gvec, atol, btol, ctol, itnlim, force_iters);
+  }
+  const int kPoll = gexec ? 4 : 1;
+  int launched = 0;
+  while (!h_stop) {
+    for (int k = 0; k < kPoll; k++) {
+      if (gexec) {
+        DS_CUDA(cudaGraphLaunch(gexec, st));
+      } else {
+        DS_CHECK(enqueue_iteration(s, damp, atol, btol, ctol, itnlim, force_iters, localVecs, dist));
+      }
+      launched++;
+    }
     DS_CUDA(cudaMemcpyAsync(&h_stop, &S->stop, sizeof(int), cudaMemcpyDeviceToHost, st));
     DS_CUDA(cudaStreamSynchronize(st));
-    float ms;
-    cudaEventElapsedTime(&ms, ea, eb); t_spmv += ms;
-    cudaEventElapsedTime(&ms, ec, ed); t_spmtv += ms;
-    iters_launched++;
-    if (iters_launched > itnlim + 2) break;
+    if (launched > itnlim + 8) break;
   }
   cudaEventRecord(e1, st);
   LsmrScalars hs;
@@ -688,13 +820,33 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   if (x_host) DS_CUDA(cudaMemcpyAsync(x_host, s->x.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
   DS_CUDA(cudaStreamSynchronize(st));
   DS_CUDA(cudaGetLastError());
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_total) *ms_total = ms;
-  if (ms_spmv) *ms_spmv = t_spmv;
-  if (ms_spmtv) *ms_spmtv = t_spmtv;
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ea); cudaEventDestroy(eb);
-  cudaEventDestroy(ec); cudaEventDestroy(ed);
+  // per-product timings (bench / roofline): 10 stand-alone launches each, after the solve
+  if (ms_spmv || ms_spmtv) {
+    const int reps = 10;
+    for (int which = 0; which < 2; which++) {
+      double *dst = which == 0 ? ms_spmv : ms_spmtv;
+      if (!dst) continue;
+      float *ybuf = which == 0 ? s->u.p : s->vpart.p;  // scratch outputs (solve is finished)
+      cudaEventRecord(e0, st);
+      for (int r = 0; r < reps; r++) {
+        if (which == 0)
+          launch_product(st, s->A, s->v.p, ybuf, nullptr, 0.0f, nullptr, nullptr);
+        else
+          launch_product(st, s->At, s->u.p, ybuf, nullptr, 0.0f, nullptr, nullptr);
+      }
+      cudaEventRecord(e1, st);
+      DS_CUDA(cudaStreamSynchronize(st));
+      cudaEventElapsedTime(&ms, e0, e1);
+      *dst = (double)ms / reps * (double)hs.itn;  // scaled to the iteration count like before
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   int is = hs.istop;
   if (damp > 0.0f && is == 2) is = 3;  // lsmrModule.f90:654
   if (istop) *istop = is;
@@ -718,9 +870,7 @@ extern "C" int dsurf_aprod(int mode, int m, int n, float *x, float *y, int leniw
   if (leniw < 2 * nar + 1 || lenrw < nar) return DSURF_ERR_BAD_ARG;
   DevBuf<int> dr, dc;
   DevBuf<float> dv, dx, dy;
-  DevBuf<long long> ptr;
-  DevBuf<int> idx;
-  DevBuf<float> val;
+  Compressed C;
   const size_t nn = nar > 0 ? nar : 1;
   if (dr.reserve(nn) || dc.reserve(nn) || dv.reserve(nn) || dx.reserve(n) || dy.reserve(m)) return DSURF_ERR_CUDA;
   DS_CUDA(cudaMemcpy(dr.p, iw + 1, nar * sizeof(int), cudaMemcpyHostToDevice));
@@ -733,14 +883,14 @@ extern "C" int dsurf_aprod(int mode, int m, int n, float *x, float *y, int leniw
   const float h1 = 1.0f;
   DS_CUDA(cudaMemcpy(one.p, &h1, sizeof(float), cudaMemcpyHostToDevice));
   if (mode == 1) {
-    DS_CHECK(build_compressed(0, dr.p, dc.p, dv.p, nar, m, ptr, idx, val));
-    k_spmv_warp<<<(m + kSpmvWarps - 1) / kSpmvWarps, kSpmvWarps * 32>>>(ptr.p, idx.p, val.p, dx.p, dy.p,
-                                                                        one.p, 1.0f, m, nullptr, nullptr);
+    DS_CHECK(build_compressed(0, dr.p, dc.p, dv.p, nar, m, C.ptr, C.idx, C.val));
+    DS_CHECK(classify_rows(0, C, m));
+    launch_product(0, C, dx.p, dy.p, one.p, 1.0f, nullptr, nullptr);
     DS_CUDA(cudaMemcpy(y, dy.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost));
   } else {
-    DS_CHECK(build_compressed(0, dc.p, dr.p, dv.p, nar, n, ptr, idx, val));
-    k_spmv_warp<<<(n + kSpmvWarps - 1) / kSpmvWarps, kSpmvWarps * 32>>>(ptr.p, idx.p, val.p, dy.p, dx.p,
-                                                                        one.p, 1.0f, n, nullptr, nullptr);
+    DS_CHECK(build_compressed(0, dc.p, dr.p, dv.p, nar, n, C.ptr, C.idx, C.val));
+    DS_CHECK(classify_rows(0, C, n));
+    launch_product(0, C, dy.p, dx.p, one.p, 1.0f, nullptr, nullptr);
     DS_CUDA(cudaMemcpy(x, dx.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
   }
   DS_CUDA(cudaGetLastError());
