@@ -869,6 +869,472 @@ k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__
   if (rc < 0 && lane == 0) sw[slot].status = DSURF_ERR_HEAP;
 }
 
+
+// =============================================================================================
+// v3: kG lanes per sweep, 32/kG sweeps per warp.  The march is serial per sweep, so with one warp
+// per sweep (v1/v2) 31 of 32 lanes replay the same scalar work (ncu: ~780 warp instructions per
+// accepted node, issue-bound at full occupancy).  Here eight lanes own a sweep: the scalar heap
+// work is still executed redundantly, but only 8-wide, and four sweeps share every issued
+// instruction.  Lane roles inside a group (gl = lane % 8):
+//   * stencil: lane gl loads stencil node gl of each of the four neighbours (4 independent loads);
+//     they are exchanged through a 256-byte shared scratch so that lane gl ends up with the eight
+//     stencil nodes of neighbour gl/2 and solves two of its four quadrants;
+//   * sift-down below the shared-memory heap levels: three levels (14 entries) are fetched by the
+//     group in one round trip into the scratch and walked from there;
+//   * sift-up: lane gl fetches ancestor (gl&1) of neighbour gl/2's heap slot in one round trip.
+// Pop order, arithmetic and tie behaviour are those of march<> / march2<> (bit-identical output).
+// =============================================================================================
+constexpr int kG = 8;
+constexpr int kNG = 32 / kG;
+constexpr int kHS3 = 256;
+constexpr int kScr = 32;  // int2 scratch entries per sweep
+
+template <bool REFINED>
+__device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, int hcap, int gl, unsigned gm,
+                      int gbase, int vnl, int vnr, int vnt, int vnb) {
+  const int nnx = G.nnx, nnz = G.nnz;
+  int2 lastE = make_int2(0, 0);
+  bool lastOK = false;
+  const int Xown = gl >> 1;  // neighbour whose quadrants this lane solves
+  while (ntr > 0) {
+    const int root = H.sm[1].y;
+    const int ix = root / nnz + 1, iz = root - (ix - 1) * nnz + 1;
+    if (REFINED) {
+      int swrg = 0;
+      if (ix == 1 && vnl != 1) swrg = 1;
+      if (ix == nnx && vnr != nnx) swrg = 1;  // sic (:399-401)
+      if (iz == 1 && vnt != 1) swrg = 1;
+      if (iz == nnz && vnb != nnz) swrg = 1;
+      if (swrg) {
+        G.node[root].y = 0;
+        break;
+      }
+    }
+    G.node[root].y = 0;
+    // ---- ids of the four neighbours (group-uniform)
+    const int xid0 = (ix - 1 >= 1) ? (ix - 2) * nnz + (iz - 1) : -1;
+    const int xid1 = (ix + 1 <= nnx) ? ix * nnz + (iz - 1) : -1;
+    const int xid2 = (iz - 1 >= 1) ? (ix - 1) * nnz + (iz - 2) : -1;
+    const int xid3 = (iz + 1 <= nnz) ? (ix - 1) * nnz + iz : -1;
+    // ---- (1) loads: own neighbour record + stencil node gl of each neighbour
+    const int oxx = ix + (Xown == 0 ? -1 : Xown == 1 ? 1 : 0);
+    const int oxz = iz + (Xown == 2 ? -1 : Xown == 3 ? 1 : 0);
+    const int oidx = (Xown == 0) ? xid0 : (Xown == 1) ? xid1 : (Xown == 2) ? xid2 : xid3;
+    int2 xn = make_int2(0, 0);
+    float velx = 1.0f, risti = 0.0f;
+    if (oidx >= 0) {
+      xn = G.node[oidx];
+      velx = G.vel[oidx];
+      risti = G.risti[oxx - 1];
+    }
+    (void)oxz;
+    int2 sn[4];
+    {
+      const int off = (gl & 1) ? 2 : 1;
+      const int sgn = (gl & 2) ? 1 : -1;
+      const int ddx = (gl < 4) ? sgn * off : 0;
+      const int ddz = (gl < 4) ? 0 : sgn * off;
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const int xx = ix + (g == 0 ? -1 : g == 1 ? 1 : 0);
+        const int xz = iz + (g == 2 ? -1 : g == 3 ? 1 : 0);
+        const bool xin = (xx >= 1 && xx <= nnx && xz >= 1 && xz <= nnz);
+        const int sx = xx + ddx, sz = xz + ddz;
+        sn[g] = make_int2(0, kOut);
+        if (xin && sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz) sn[g] = G.node[(sx - 1) * nnz + (sz - 1)];
+      }
+    }
+    int xm0 = -1, xm1 = -1, xm2 = -1, xm3 = -1;
+#define TRACK_MOVE(nid, newpos)        \
+  {                                    \
+    if ((nid) == xid0) xm0 = (newpos); \
+    if ((nid) == xid1) xm1 = (newpos); \
+    if ((nid) == xid2) xm2 = (newpos); \
+    if ((nid) == xid3) xm3 = (newpos); \
+  }
+    // ---- (2) downtree (:816-885)
+    if (ntr == 1) {
+      ntr = 0;
+      lastOK = false;
+    } else {
+      const int2 m = lastOK ? lastE : H.get(ntr);
+      const float mk = keyf(m);
+      ntr = ntr - 1;
+      int tpp = 1, tpc = 2;
+      bool stop = false;
+      while (!stop && tpc < ntr && tpc + 1 < kHS3) {
+        const int2 e1 = H.sm[tpc], e2 = H.sm[tpc + 1];
+        int2 ec = e1;
+        if (keyf(e1) > keyf(e2)) {
+          tpc = tpc + 1;
+          ec = e2;
+        }
+        if (keyf(ec) < mk) {
+          H.sm[tpp] = ec;
+          G.node[ec.y].y = tpp;
+          TRACK_MOVE(ec.y, tpp);
+          tpp = tpc;
+          tpc = 2 * tpp;
+        } else {
+          stop = true;
+        }
+      }
+      while (!stop && tpc <= ntr) {
+        if (tpc + 1 < kHS3) {  // single child inside shared memory (tpc == ntr)
+          const int2 e1 = H.sm[tpc];
+          if (keyf(e1) < mk) {
+            H.sm[tpp] = e1;
+            G.node[e1.y].y = tpp;
+            TRACK_MOVE(e1.y, tpp);
+            tpp = tpc;
+          }
+          stop = true;
+          break;
+        }
+        // three levels below tpp -> scratch[(2^r - 2) + o], r = 1..3
+#pragma unroll
+        for (int t0 = 0; t0 < 16; t0 += kG) {
+          const int t = t0 + gl;
+          if (t < 14) {
+            const int r = (t < 2) ? 1 : (t < 6) ? 2 : 3;
+            const int o = t - ((1 << r) - 2);
+            const long long pos = ((long long)tpp << r) + o;
+            int2 e = make_int2(0x7f800000, -1);
+            if (pos <= ntr) e = H.get((int)pos);
+            scr[t] = e;
+          }
+        }
+        __syncwarp(gm);
+        const int base = tpp;
+        int rel = 0;
+        for (int lvl = 1; lvl <= 3; lvl++) {
+          const long long c0 = ((long long)base << lvl) + 2 * rel;
+          if (c0 > ntr) {
+            stop = true;
+            break;
+          }
+          const int Lc = (1 << lvl) - 2 + 2 * rel;
+          const int2 e1 = scr[Lc], e2 = scr[Lc + 1];
+          int pick = 0;
+          if (c0 < ntr && keyf(e1) > keyf(e2)) pick = 1;
+          const int2 ec = pick ? e2 : e1;
+          if (keyf(ec) < mk) {
+            H.set(tpp, ec);
+            G.node[ec.y].y = tpp;
+            TRACK_MOVE(ec.y, tpp);
+            tpp = (int)c0 + pick;
+            rel = 2 * rel + pick;
+            if (c0 == ntr) {
+              stop = true;
+              break;
+            }
+          } else {
+            stop = true;
+            break;
+          }
+        }
+        __syncwarp(gm);
+        tpc = 2 * tpp;
+      }
+      H.set(tpp, m);
+      G.node[m.y].y = tpp;
+      TRACK_MOVE(m.y, tpp);
+      lastOK = false;
+    }
+#undef TRACK_MOVE
+    // ---- stencil exchange through the scratch: lane gl receives the 8 nodes of neighbour gl/2
+#pragma unroll
+    for (int g = 0; g < 4; g++) scr[g * 8 + gl] = sn[g];
+    __syncwarp(gm);
+    int2 s8[8];
+#pragma unroll
+    for (int qq = 0; qq < 8; qq++) s8[qq] = scr[Xown * 8 + qq];
+    __syncwarp(gm);
+    // ---- quadrants: this lane solves (jside = gl & 1, kside = 0 and 1) of neighbour Xown
+    const int proc = (oidx >= 0 && xn.y != 0) ? (xn.y == -1 ? 1 : 2) : 0;
+    float trav = 3.0e38f;
+    if (proc) {
+      const float slown = 1.0f / velx;
+      const int js = gl & 1;
+      const int2 nj = js ? s8[2] : s8[0], nj2 = js ? s8[3] : s8[1];
+      if (nj.y != kOut) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          const int2 nk = ks ? s8[6] : s8[4], nk2 = ks ? s8[7] : s8[5];
+          if (nk.y != kOut) {
+            float tq;
+            if (quadrant(__int_as_float(nj.x), __int_as_float(nj2.x), nj.y, nj2.y, __int_as_float(nk.x),
+                         __int_as_float(nk2.x), nk.y, nk2.y, slown, G.earth, risti, G.dnx, G.dnz, tq))
+              trav = fminf(trav, tq);
+          }
+        }
+      }
+    }
+    trav = fminf(trav, __shfl_xor_sync(gm, trav, 1));
+    // ---- (3) planned heap positions + ancestor fetch
+    int pr[4], xi[4], ppos[4];
+    float tv[4];
+    int nfar = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      pr[g] = __shfl_sync(gm, proc, gbase + 2 * g);
+      tv[g] = __shfl_sync(gm, trav, gbase + 2 * g);
+      const int st = __shfl_sync(gm, xn.y, gbase + 2 * g);
+      xi[g] = (g == 0) ? xid0 : (g == 1) ? xid1 : (g == 2) ? xid2 : xid3;
+      const int xm = (g == 0) ? xm0 : (g == 1) ? xm1 : (g == 2) ? xm2 : xm3;
+      ppos[g] = 0;
+      if (pr[g] == 1) {
+        nfar++;
+        ppos[g] = ntr + nfar;
+      } else if (pr[g] == 2) {
+        ppos[g] = (xm >= 0) ? xm : st;
+      }
+    }
+    const int mypos = (Xown == 0) ? ppos[0] : (Xown == 1) ? ppos[1] : (Xown == 2) ? ppos[2] : ppos[3];
+    const int myanc = mypos >> ((gl & 1) + 1);
+    int2 anc = make_int2(0, -1);
+    if (myanc >= 1) anc = H.get(myanc);
+    int2 cand = make_int2(0, -1);
+    if (nfar == 0 && ntr >= 1) cand = H.get(ntr);
+    // ---- apply in the reference's order (:424-486)
+    bool slow = false;
+    int ls0 = -1, ls1 = -1, ls2 = -1, ls3 = -1;
+    int2 le0 = make_int2(0, 0), le1 = le0, le2 = le0, le3 = le0;
+    int nl = 0;
+    bool appended = false;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      if (!pr[g]) continue;
+      const int xg = xi[g];
+      const float tvg = tv[g];
+      G.node[xg].x = __float_as_int(tvg);
+      int tpc;
+      if (pr[g] == 1) {
+        ntr = ntr + 1;
+        if (ntr > hcap) return -1;
+        tpc = ntr;
+      } else {
+        tpc = slow ? G.node[xg].y : ppos[g];
+      }
+      const bool use_pref = !slow && (tpc == ppos[g]);
+      int a = 0;
+      bool moved = false;
+      int tpp = tpc >> 1;
+      while (tpp > 0) {
+        int2 pe;
+        if (use_pref && a < 2) {
+          pe.x = __shfl_sync(gm, anc.x, gbase + 2 * g + a);
+          pe.y = __shfl_sync(gm, anc.y, gbase + 2 * g + a);
+          if (tpp == ls0) pe = le0;
+          if (tpp == ls1) pe = le1;
+          if (tpp == ls2) pe = le2;
+        } else {
+          pe = H.get(tpp);
+        }
+        if (tvg < keyf(pe)) {
+          H.set(tpc, pe);
+          G.node[pe.y].y = tpc;
+          tpc = tpp;
+          tpp = tpc >> 1;
+          a++;
+          moved = true;
+        } else {
+          tpp = 0;
+        }
+      }
+      const int2 ne = make_int2(__float_as_int(tvg), xg);
+      H.set(tpc, ne);
+      G.node[xg].y = tpc;
+      if (moved) {
+        slow = true;
+      } else {
+        if (nl == 0) { ls0 = tpc; le0 = ne; }
+        if (nl == 1) { ls1 = tpc; le1 = ne; }
+        if (nl == 2) { ls2 = tpc; le2 = ne; }
+        if (nl == 3) { ls3 = tpc; le3 = ne; }
+        nl++;
+      }
+      if (pr[g] == 1) {
+        appended = true;
+        lastE = ne;
+        lastOK = !moved;
+      }
+    }
+    if (!appended) {
+      if (!slow && ntr >= 1) {
+        lastE = cand;
+        if (ntr == ls0) lastE = le0;
+        if (ntr == ls1) lastE = le1;
+        if (ntr == ls2) lastE = le2;
+        if (ntr == ls3) lastE = le3;
+        lastOK = true;
+      } else {
+        lastOK = false;
+      }
+    } else if (slow) {
+      lastOK = false;
+    }
+  }
+  return ntr;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
+           const float *__restrict__ velv_all, const float *__restrict__ risti_c, BatchView bv) {
+  extern __shared__ float smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gg = lane / kG, gl = lane % kG, gbase = gg * kG;
+  const unsigned gm = ((1u << kG) - 1u) << gbase;
+  const int slot = (blockIdx.x * kWarpsPerBlock + w) * kNG + gg;
+  if (slot >= nsw) return;
+  int2 *wbase = (int2 *)smem + (size_t)w * kNG * (kHS3 + kScr);
+  Heap2<kHS3> H;
+  H.sm = wbase + (size_t)gg * kHS3;
+  H.gm = bv.hent + (size_t)slot * (bv.hcap + 1);
+  int2 *scr = wbase + (size_t)kNG * kHS3 + (size_t)gg * kScr;
+  SweepDesc d = sw[slot];
+  const size_t Nc = (size_t)g.nnx * g.nnz;
+  const float *veln = veln_all + (size_t)d.map * Nc;
+  const float *velv = velv_all + (size_t)d.map * g.nx * g.ny;
+  int2 *node = bv.node + (size_t)slot * Nc;
+  int2 *noder = bv.noder + (size_t)slot * kRefMax * kRefMax;
+  float *velr = bv.velr + (size_t)slot * kRefMax * kRefMax;
+  const int nrnx = d.nrnx, nrnz = d.nrnz;
+  // ---- bsplrefine (:1562-1628)
+  {
+    const int nrr = kGd * kSgdl;
+    const int origx = (d.vnl - 1) * kSgdl + 1, origz = (d.vnt - 1) * kSgdl + 1;
+    const int ldv = g.nvx + 2;
+    for (int n = gl; n < nrnx * nrnz; n += kG) {
+      const int idm1 = n % nrnz + 1, idm2 = n / nrnz + 1;
+      const int st1 = idm1 + origz - 1, st2 = idm2 + origx - 1;
+      int i = (st1 - 1) / nrr + 1;
+      if (i > g.nvz - 1) i = g.nvz - 1;
+      const int k = st1 - nrr * (i - 1);
+      int j = (st2 - 1) / nrr + 1;
+      if (j > g.nvx - 1) j = g.nvx - 1;
+      const int l = st2 - nrr * (j - 1);
+      float ul[4], vk[4];
+      bspline4((float)(l - 1) / (float)nrr, ul);
+      bspline4((float)(k - 1) / (float)nrr, vk);
+      float s[4];
+#pragma unroll
+      for (int i1 = 0; i1 < 4; i1++) {
+        float t = 0.0f;
+#pragma unroll
+        for (int j1 = 0; j1 < 4; j1++) t = t + ul[j1] * velv[(i - 1 + i1) * ldv + (j - 1 + j1)];
+        s[i1] = vk[i1] * t;
+      }
+      velr[n] = s[0] + s[1] + s[2] + s[3];
+      noder[n] = make_int2(0, -1);
+    }
+  }
+  __syncwarp(gm);
+  Grid R;
+  R.node = noder;
+  R.vel = velr;
+  R.risti = bv.ristr + (size_t)slot * kRefMax;
+  R.nnx = nrnx;
+  R.nnz = nrnz;
+  R.dnx = g.drnx;
+  R.dnz = g.drnz;
+  R.earth = g.earth;
+  int ntr = 0;
+  {
+    const int isx = d.tsx, isz = d.tsz;
+    float vss[2][2];
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) vss[i][j] = velr[(isx - 1 + i) * nrnz + (isz - 1 + j)];
+    const float dsx = (d.scx - d.gorx) - (float)(isx - 1) * g.drnx;
+    const float dsz = (d.scz - d.gorz) - (float)(isz - 1) * g.drnz;
+    float vsrc = 0.0f;
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) {
+        const float produ = (1.0f - fabsf(((float)i * g.drnx - dsx) / g.drnx)) *
+                            (1.0f - fabsf(((float)j * g.drnz - dsz) / g.drnz));
+        vsrc = vsrc + vss[i][j] * produ;
+      }
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) {
+        const float ex = dsx - (float)i * g.drnx, ez = dsz - (float)j * g.drnz;
+        const float ds = sqrtf(ex * ex + ez * ez);
+        const float t0 = 2.0f * ds / (vss[i][j] + vsrc);
+        const int xi = (isx - 1 + i) * nrnz + (isz - 1 + j);
+        noder[xi].x = __float_as_int(t0);
+        ntr = ntr + 1;
+        sift_up2(H, R, ntr, t0, xi);
+      }
+  }
+  int rc = march3<true>(R, H, scr, ntr, bv.hcap, gl, gm, gbase, d.vnl, d.vnr, d.vnt, d.vnb);
+  if (rc < 0) {
+    if (gl == 0) sw[slot].status = DSURF_ERR_HEAP;
+    return;
+  }
+  __syncwarp(gm);
+  const int bw = d.vnr - d.vnl + 1, bh = d.vnb - d.vnt + 1;
+  for (int n = gl; n < bw * bh; n += kG) {
+    const int cz = n % bh, cx = n / bh;
+    const int2 rn = noder[(cx * kSgdl) * nrnz + cz * kSgdl];
+    int2 cn = make_int2(0, rn.y);
+    if (rn.y >= 0) cn.x = rn.x;
+    node[(size_t)(d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz)] = cn;
+  }
+  __syncwarp(gm);
+  for (int n = gl; n < bw * bh; n += kG) {
+    const int cz = n % bh, cx = n / bh;
+    const int k = d.vnl + cx, l = d.vnt + cz;
+    const size_t o = (size_t)(k - 1) * g.nnz + (l - 1);
+    if (node[o].y == 0) {
+      bool far = false;
+      if (l - 1 >= 1 && node[o - 1].y == -1) far = true;
+      if (l + 1 <= g.nnz && node[o + 1].y == -1) far = true;
+      if (k - 1 >= 1 && node[o - g.nnz].y == -1) far = true;
+      if (k + 1 <= g.nnx && node[o + g.nnz].y == -1) far = true;
+      if (far) node[o].y = -100;
+    }
+  }
+  __syncwarp(gm);
+  for (int n = gl; n < bw * bh; n += kG) {
+    const int cz = n % bh, cx = n / bh;
+    const size_t o = (size_t)(d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz);
+    if (node[o].y == -100) node[o].y = 1;
+  }
+  __syncwarp(gm);
+  Grid C;
+  C.node = node;
+  C.vel = veln;
+  C.risti = risti_c;
+  C.nnx = g.nnx;
+  C.nnz = g.nnz;
+  C.dnx = g.dnx;
+  C.dnz = g.dnz;
+  C.earth = g.earth;
+  ntr = 0;
+  for (int cx = 0; cx < bw; cx++) {
+    for (int base = 0; base < bh; base += kG) {
+      const int cz = base + gl;
+      int st = 0;
+      float tt = 0.0f;
+      if (cz < bh) {
+        const int2 v = node[(size_t)(d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz)];
+        st = v.y;
+        tt = __int_as_float(v.x);
+      }
+      unsigned mask = (__ballot_sync(gm, st > 0) >> gbase) & ((1u << kG) - 1u);
+      while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float key = __shfl_sync(gm, tt, gbase + b);
+        const int xi = (d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + base + b);
+        ntr = ntr + 1;
+        sift_up2(H, C, ntr, key, xi);
+      }
+    }
+  }
+  rc = march3<false>(C, H, scr, ntr, bv.hcap, gl, gm, gbase, 0, 0, 0, 0);
+  if (rc < 0 && gl == 0) sw[slot].status = DSURF_ERR_HEAP;
+}
+
 constexpr int kHeapSm2 = 768;  // v2: 6 KB of heap per warp -> 4 blocks (32 warps) per SM
 
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
@@ -876,7 +1342,22 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
   if (nsw <= 0) return DSURF_OK;
   const long long ntot = (long long)nsw * g.nnx * g.nnz;
   k_fill_nodes<<<sm_count() * 8, kWarpsPerBlock * 32, 0, st>>>(bv.node, ntot);
-  static const bool use_v1 = getenv("DSURF_EIKONAL_V1") != nullptr;  // reference variant for A/B tests
+  static const bool use_v1 = getenv("DSURF_EIKONAL_V1") != nullptr;  // reference variants for A/B tests
+  static const bool use_v2 = getenv("DSURF_EIKONAL_V2") != nullptr;
+  if (!use_v1 && !use_v2) {
+    const size_t smem = (size_t)kWarpsPerBlock * kNG * (kHS3 + kScr) * sizeof(int2);
+    static bool attr3 = false;
+    if (!attr3) {
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr3 = true;
+    }
+    const int per_block = kWarpsPerBlock * kNG;
+    k_eikonal3<<<(nsw + per_block - 1) / per_block, kWarpsPerBlock * 32, smem, st>>>(
+        g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all, d_velv_all, d_risti, bv);
+    DS_CUDA(cudaGetLastError());
+    if (launches) *launches += 2;
+    return DSURF_OK;
+  }
   const int grid = (nsw + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (use_v1) {
     const size_t smem = (size_t)kWarpsPerBlock * 2 * kHeapSm * sizeof(float);

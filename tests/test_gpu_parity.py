@@ -247,14 +247,17 @@ def test_outer_iteration_model_update(taipei):
     assert np.abs(vs_new / vs_ref - 1).max() <= 1e-5
 
 
-def test_reference_eikonal_variant_also_bit_exact():
-    """The simple (v1) march and the overlapped (v2) march must both reproduce the oracle; v1 is
-    selected with DSURF_EIKONAL_V1=1 at process start."""
+@pytest.mark.parametrize("var", ["DSURF_EIKONAL_V1", "DSURF_EIKONAL_V2"])
+def test_reference_eikonal_variants_also_bit_exact(var):
+    """The simple (v1: one warp per sweep), overlapped (v2) and sub-warp (v3, default: 8 lanes per
+    sweep) marches must all reproduce the oracle; v1/v2 are selected by an environment variable at
+    process start."""
     import os
     import subprocess
     import sys
 
-    env = dict(os.environ, DSURF_EIKONAL_V1="1")
+    env = dict(os.environ)
+    env[var] = "1"
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
                         "-k", "sweep_bit_exact or calsurfg_small"], env=env, capture_output=True, text=True)
