@@ -884,19 +884,35 @@ k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__
 //   * sift-up: lane gl fetches ancestor (gl&1) of neighbour gl/2's heap slot in one round trip.
 // Pop order, arithmetic and tie behaviour are those of march<> / march2<> (bit-identical output).
 // =============================================================================================
-constexpr int kG = 8;
-constexpr int kNG = 32 / kG;
-constexpr int kHS3 = 256;
 constexpr int kScr = 32;  // int2 scratch entries per sweep
+// kG lanes per sweep (8 or 16); HS shared-memory heap entries per sweep
+template <int kG> struct V3 {
+  static constexpr int NG = 32 / kG;          // sweeps per warp
+  static constexpr int LPX = kG / 4;          // lanes per neighbour
+  static constexpr int NQ = 16 / kG;          // quadrants per lane
+  static constexpr int HS = (kG == 16) ? 384 : 256;
+  static constexpr int MINB = (kG == 16) ? 4 : 3;  // resident blocks per SM aimed at
+};
 
-template <bool REFINED>
-__device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, int hcap, int gl, unsigned gm,
-                      int gbase, int vnl, int vnr, int vnt, int vnb) {
+template <bool REFINED, int kG>
+__device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int ntr, int hcap, int gl, unsigned gm,
+                      int gbase, unsigned wmask, int vnl, int vnr, int vnt, int vnb) {
   const int nnx = G.nnx, nnz = G.nnz;
   int2 lastE = make_int2(0, 0);
   bool lastOK = false;
-  const int Xown = gl >> 1;  // neighbour whose quadrants this lane solves
-  while (ntr > 0) {
+  constexpr int kHS3 = V3<kG>::HS, LPX = V3<kG>::LPX, NQ = V3<kG>::NQ;
+  const int Xown = gl / LPX;  // neighbour whose quadrants this lane solves
+  const int sub = gl % LPX;   // index of this lane among the lanes of its neighbour
+  bool active = ntr > 0;
+  int err = 0;
+  // The four sweeps of a warp advance in lock step: without the warp-wide barrier at the top of
+  // every acceptance the groups drift apart and the warp ends up replaying each group's
+  // instruction stream separately (measured: no gain over one sweep per warp).
+  for (;;) {
+    __syncwarp(wmask);
+    if (!__any_sync(wmask, active)) break;
+    if (!active) continue;
+    do {
     const int root = H.sm[1].y;
     const int ix = root / nnz + 1, iz = root - (ix - 1) * nnz + 1;
     if (REFINED) {
@@ -907,6 +923,7 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
       if (iz == nnz && vnb != nnz) swrg = 1;
       if (swrg) {
         G.node[root].y = 0;
+        active = false;
         break;
       }
     }
@@ -928,20 +945,22 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
       risti = G.risti[oxx - 1];
     }
     (void)oxz;
-    int2 sn[4];
+    int2 sn[32 / kG];
     {
-      const int off = (gl & 1) ? 2 : 1;
-      const int sgn = (gl & 2) ? 1 : -1;
-      const int ddx = (gl < 4) ? sgn * off : 0;
-      const int ddz = (gl < 4) ? 0 : sgn * off;
+      const int qn = gl & 7;  // stencil node handled by this lane
+      const int off = (qn & 1) ? 2 : 1;
+      const int sgn = (qn & 2) ? 1 : -1;
+      const int ddx = (qn < 4) ? sgn * off : 0;
+      const int ddz = (qn < 4) ? 0 : sgn * off;
 #pragma unroll
-      for (int g = 0; g < 4; g++) {
+      for (int j = 0; j < 32 / kG; j++) {
+        const int g = ((gl + kG * j) >> 3);  // neighbour of item t = gl + kG*j
         const int xx = ix + (g == 0 ? -1 : g == 1 ? 1 : 0);
         const int xz = iz + (g == 2 ? -1 : g == 3 ? 1 : 0);
         const bool xin = (xx >= 1 && xx <= nnx && xz >= 1 && xz <= nnz);
         const int sx = xx + ddx, sz = xz + ddz;
-        sn[g] = make_int2(0, kOut);
-        if (xin && sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz) sn[g] = G.node[(sx - 1) * nnz + (sz - 1)];
+        sn[j] = make_int2(0, kOut);
+        if (xin && sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz) sn[j] = G.node[(sx - 1) * nnz + (sz - 1)];
       }
     }
     int xm0 = -1, xm1 = -1, xm2 = -1, xm3 = -1;
@@ -1044,7 +1063,7 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
 #undef TRACK_MOVE
     // ---- stencil exchange through the scratch: lane gl receives the 8 nodes of neighbour gl/2
 #pragma unroll
-    for (int g = 0; g < 4; g++) scr[g * 8 + gl] = sn[g];
+    for (int j = 0; j < 32 / kG; j++) scr[gl + kG * j] = sn[j];
     __syncwarp(gm);
     int2 s8[8];
 #pragma unroll
@@ -1055,31 +1074,31 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
     float trav = 3.0e38f;
     if (proc) {
       const float slown = 1.0f / velx;
-      const int js = gl & 1;
-      const int2 nj = js ? s8[2] : s8[0], nj2 = js ? s8[3] : s8[1];
-      if (nj.y != kOut) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ks++) {
-          const int2 nk = ks ? s8[6] : s8[4], nk2 = ks ? s8[7] : s8[5];
-          if (nk.y != kOut) {
-            float tq;
-            if (quadrant(__int_as_float(nj.x), __int_as_float(nj2.x), nj.y, nj2.y, __int_as_float(nk.x),
-                         __int_as_float(nk2.x), nk.y, nk2.y, slown, G.earth, risti, G.dnx, G.dnz, tq))
-              trav = fminf(trav, tq);
-          }
+      for (int qq = 0; qq < NQ; qq++) {
+        const int r = sub * NQ + qq;  // quadrant index: jside = r >> 1, kside = r & 1
+        const int js = r >> 1, ks = r & 1;
+        const int2 nj = js ? s8[2] : s8[0], nj2 = js ? s8[3] : s8[1];
+        const int2 nk = ks ? s8[6] : s8[4], nk2 = ks ? s8[7] : s8[5];
+        if (nj.y != kOut && nk.y != kOut) {
+          float tq;
+          if (quadrant(__int_as_float(nj.x), __int_as_float(nj2.x), nj.y, nj2.y, __int_as_float(nk.x),
+                       __int_as_float(nk2.x), nk.y, nk2.y, slown, G.earth, risti, G.dnx, G.dnz, tq))
+            trav = fminf(trav, tq);
         }
       }
     }
-    trav = fminf(trav, __shfl_xor_sync(gm, trav, 1));
+#pragma unroll
+    for (int o = 1; o < LPX; o <<= 1) trav = fminf(trav, __shfl_xor_sync(gm, trav, o));
     // ---- (3) planned heap positions + ancestor fetch
     int pr[4], xi[4], ppos[4];
     float tv[4];
     int nfar = 0;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-      pr[g] = __shfl_sync(gm, proc, gbase + 2 * g);
-      tv[g] = __shfl_sync(gm, trav, gbase + 2 * g);
-      const int st = __shfl_sync(gm, xn.y, gbase + 2 * g);
+      pr[g] = __shfl_sync(gm, proc, gbase + LPX * g);
+      tv[g] = __shfl_sync(gm, trav, gbase + LPX * g);
+      const int st = __shfl_sync(gm, xn.y, gbase + LPX * g);
       xi[g] = (g == 0) ? xid0 : (g == 1) ? xid1 : (g == 2) ? xid2 : xid3;
       const int xm = (g == 0) ? xm0 : (g == 1) ? xm1 : (g == 2) ? xm2 : xm3;
       ppos[g] = 0;
@@ -1091,11 +1110,16 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
       }
     }
     const int mypos = (Xown == 0) ? ppos[0] : (Xown == 1) ? ppos[1] : (Xown == 2) ? ppos[2] : ppos[3];
-    const int myanc = mypos >> ((gl & 1) + 1);
+    const int myanc = mypos >> (sub + 1);
     int2 anc = make_int2(0, -1);
     if (myanc >= 1) anc = H.get(myanc);
     int2 cand = make_int2(0, -1);
     if (nfar == 0 && ntr >= 1) cand = H.get(ntr);
+    if (ntr + nfar > hcap) {
+      err = -1;
+      active = false;
+      break;
+    }
     // ---- apply in the reference's order (:424-486)
     bool slow = false;
     int ls0 = -1, ls1 = -1, ls2 = -1, ls3 = -1;
@@ -1111,7 +1135,6 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
       int tpc;
       if (pr[g] == 1) {
         ntr = ntr + 1;
-        if (ntr > hcap) return -1;
         tpc = ntr;
       } else {
         tpc = slow ? G.node[xg].y : ppos[g];
@@ -1122,9 +1145,9 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
       int tpp = tpc >> 1;
       while (tpp > 0) {
         int2 pe;
-        if (use_pref && a < 2) {
-          pe.x = __shfl_sync(gm, anc.x, gbase + 2 * g + a);
-          pe.y = __shfl_sync(gm, anc.y, gbase + 2 * g + a);
+        if (use_pref && a < LPX) {
+          pe.x = __shfl_sync(gm, anc.x, gbase + LPX * g + a);
+          pe.y = __shfl_sync(gm, anc.y, gbase + LPX * g + a);
           if (tpp == ls0) pe = le0;
           if (tpp == ls1) pe = le1;
           if (tpp == ls2) pe = le2;
@@ -1174,18 +1197,23 @@ __device__ int march3(const Grid &G, const Heap2<kHS3> &H, int2 *scr, int ntr, i
     } else if (slow) {
       lastOK = false;
     }
+    if (ntr == 0) active = false;
+    } while (false);
   }
-  return ntr;
+  return err ? -1 : ntr;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int kG>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, V3<kG>::MINB)
 k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
            const float *__restrict__ velv_all, const float *__restrict__ risti_c, BatchView bv) {
   extern __shared__ float smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kNG = V3<kG>::NG, kHS3 = V3<kG>::HS;
   const int gg = lane / kG, gl = lane % kG, gbase = gg * kG;
-  const unsigned gm = ((1u << kG) - 1u) << gbase;
+  const unsigned gm = ((kG == 32) ? 0xffffffffu : ((1u << kG) - 1u)) << gbase;
   const int slot = (blockIdx.x * kWarpsPerBlock + w) * kNG + gg;
+  const unsigned wmask = __ballot_sync(kFull, slot < nsw);  // lanes of this warp that own a sweep
   if (slot >= nsw) return;
   int2 *wbase = (int2 *)smem + (size_t)w * kNG * (kHS3 + kScr);
   Heap2<kHS3> H;
@@ -1265,11 +1293,9 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
         sift_up2(H, R, ntr, t0, xi);
       }
   }
-  int rc = march3<true>(R, H, scr, ntr, bv.hcap, gl, gm, gbase, d.vnl, d.vnr, d.vnt, d.vnb);
-  if (rc < 0) {
-    if (gl == 0) sw[slot].status = DSURF_ERR_HEAP;
-    return;
-  }
+  int rc = march3<true, kG>(R, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, d.vnl, d.vnr, d.vnt, d.vnb);
+  const bool failed = rc < 0;
+  if (failed && gl == 0) sw[slot].status = DSURF_ERR_HEAP;
   __syncwarp(gm);
   const int bw = d.vnr - d.vnl + 1, bh = d.vnb - d.vnt + 1;
   for (int n = gl; n < bw * bh; n += kG) {
@@ -1331,7 +1357,8 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
       }
     }
   }
-  rc = march3<false>(C, H, scr, ntr, bv.hcap, gl, gm, gbase, 0, 0, 0, 0);
+  if (failed) ntr = 0;  // keep taking part in the warp-wide barriers of the coarse march
+  rc = march3<false, kG>(C, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, 0, 0, 0, 0);
   if (rc < 0 && gl == 0) sw[slot].status = DSURF_ERR_HEAP;
 }
 
@@ -1344,16 +1371,28 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
   k_fill_nodes<<<sm_count() * 8, kWarpsPerBlock * 32, 0, st>>>(bv.node, ntot);
   static const bool use_v1 = getenv("DSURF_EIKONAL_V1") != nullptr;  // reference variants for A/B tests
   static const bool use_v2 = getenv("DSURF_EIKONAL_V2") != nullptr;
+  static const char *gsel = getenv("DSURF_EIKONAL_G");  // lanes per sweep of the v3 kernel: 16 (default) or 8
   if (!use_v1 && !use_v2) {
-    const size_t smem = (size_t)kWarpsPerBlock * kNG * (kHS3 + kScr) * sizeof(int2);
+    const bool g8 = gsel && atoi(gsel) == 8;
+    const int ng = g8 ? V3<8>::NG : V3<16>::NG;
+    const int hs = g8 ? V3<8>::HS : V3<16>::HS;
+    const size_t smem = (size_t)kWarpsPerBlock * ng * (hs + kScr) * sizeof(int2);
     static bool attr3 = false;
     if (!attr3) {
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2))));
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2))));
       attr3 = true;
     }
-    const int per_block = kWarpsPerBlock * kNG;
-    k_eikonal3<<<(nsw + per_block - 1) / per_block, kWarpsPerBlock * 32, smem, st>>>(
-        g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all, d_velv_all, d_risti, bv);
+    const int per_block = kWarpsPerBlock * ng;
+    const int grid3 = (nsw + per_block - 1) / per_block;
+    if (g8)
+      k_eikonal3<8><<<grid3, kWarpsPerBlock * 32, smem, st>>>(g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all,
+                                                              d_velv_all, d_risti, bv);
+    else
+      k_eikonal3<16><<<grid3, kWarpsPerBlock * 32, smem, st>>>(g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all,
+                                                               d_velv_all, d_risti, bv);
     DS_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
     return DSURF_OK;
