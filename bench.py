@@ -46,6 +46,14 @@ def build_problem(cfg: int):
     raise SystemExit("--config must be 2 or 3")
 
 
+def stage_blocks(pb, mode):
+    """Steps: 'stage' = every gather of the CalSurfG call (one step = one full sweep stage);
+    'type' = one data-type block per step."""
+    if mode == "type":
+        return type_blocks(pb)
+    return [("all", 0, int(pb.nsrc1.sum()))]
+
+
 def type_blocks(pb):
     """Gather ranges of the data types present, in the reference's block order."""
     cum = np.concatenate([[0], np.cumsum(pb.nsrc1)]).astype(int)
@@ -151,7 +159,7 @@ def run_reference(args, pb, pv4, sen12, blocks):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def run_b200(args, pb, pv4, sen12, blocks):
+def run_b200(args, pb, pv4, sen12, blocks, tblocks):
     import torch
 
     from dsurftomo_b200 import api, dist as ddist, hostglue
@@ -236,7 +244,7 @@ def run_b200(args, pb, pv4, sen12, blocks):
 
     # ---------------- timed region 2: end to end through the host-buffer API (H2D + compute + D2H)
     last = plan.download()  # sizes the pinned output buffers from the last timed step
-    cap = int(last["nar"] * 1.6) + 1024
+    cap = int(last["nar"] * (1.05 if args.step_mode == "stage" else 1.6)) + 1024
     pin = dict(row=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
                col=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
                rw=torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy(),
@@ -271,10 +279,14 @@ def run_b200(args, pb, pv4, sen12, blocks):
     lsmr = None
     if args.lsmr_iters > 0:
         res = plan.download(out=pin)
-        r0 = int(res["row"].min()) - 1 if res["nar"] else 0
-        sub = type("P", (), {})()
-        nrows = int(res["row"].max()) - r0 if res["nar"] else 0
-        rows = (res["row"] - r0).astype(np.int32)
+        # system = the data rows of one data-type block (the first one in stage mode) + smoothing rows
+        lb = tblocks[0] if args.step_mode == "stage" else block_of(args.warmup + e2e_steps - 1)
+        r0, r1 = ddist.rows_of_gathers(pb, lb[1], lb[2])
+        lo = int(np.searchsorted(res["row"], r0, side="right"))
+        hi = int(np.searchsorted(res["row"], r1, side="right"))
+        nrows = r1 - r0
+        rows = (res["row"][lo:hi] - r0).astype(np.int32)
+        res = dict(res, col=res["col"][lo:hi], rw=res["rw"][lo:hi])
         obst = pb.obst[r0:r0 + nrows]
         cb = (obst - res["dsurf"][r0:r0 + nrows]).astype(np.float32)
         srow, scol, sval, cnt3 = hostglue.smoothing_rows(pb.nx, pb.ny, pb.nz, nrows, pb.weight)
@@ -333,9 +345,9 @@ def run_b200(args, pb, pv4, sen12, blocks):
 
         cores = os.cpu_count() or 1
         per_block = max(1, min(cores // 2, 32))
-        nsw, t = cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, 0, cores)
+        nsw, t = cpu_sweep_sample(pb, pv4, sen12, tblocks, per_block, 0, cores)
         cpu = dict(value=nsw / t, unit="sweeps/s", cores=cores, kind="port",
-                   sample=f"{per_block} gathers of each of {len(blocks)} data types ({nsw} sweeps, {t:.1f} s), "
+                   sample=f"{per_block} gathers of each of {len(tblocks)} data types ({nsw} sweeps, {t:.1f} s), "
                           "C++ restatement of the reference, g++ -O3 -fopenmp strict IEEE (no Fortran compiler here)")
         if lsmr is not None and lsmr["nnz"] <= 3e8:
             iw = hostglue.pack_iw(R, Cc)
@@ -350,8 +362,10 @@ def run_b200(args, pb, pv4, sen12, blocks):
                    ms_per_step=t_max_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="f32", data="synthetic",
                    config=dict(workload=pb.name, grid=f"{(pb.nx - 3) * 8 + 1}x{(pb.ny - 3) * 8 + 1}",
-                               step="all periods x sources of one data type per rank per step "
-                                    f"({[b[0] for b in blocks]} in rotation)",
+                               step=("one full CalSurfG sweep stage (every period x type x source) per rank per step"
+                                     if args.step_mode == "stage" else
+                                     "all periods x sources of one data type per rank per step "
+                                     f"({[b[0] for b in blocks]} in rotation)"),
                                receivers_per_gather=int(pb.nrc1.max()), parallelism=f"gathers sharded over {world} GPU(s)",
                                l2="per-step working set (node states of thousands of sweeps, GBs) >> 126 MB L2",
                                interpretation="A: quoted grid = FMM propagation grid (SURVEY.md section 8)"),
@@ -371,7 +385,8 @@ def run_b200(args, pb, pv4, sen12, blocks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--step-mode", default="stage", choices=["stage", "type"])
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=3)
@@ -383,11 +398,12 @@ def main():
         return 0
     pb = build_problem(args.config)
     pv4, sen12 = inputs.synthetic_dispersion(pb)
-    blocks = type_blocks(pb)
+    blocks = stage_blocks(pb, args.step_mode)
+    tblocks = type_blocks(pb)
     if args.impl == "reference":
-        run_reference(args, pb, pv4, sen12, blocks)
+        run_reference(args, pb, pv4, sen12, tblocks)
     else:
-        run_b200(args, pb, pv4, sen12, blocks)
+        run_b200(args, pb, pv4, sen12, blocks, tblocks)
     return 0
 
 

@@ -1364,6 +1364,38 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
 
 constexpr int kHeapSm2 = 768;  // v2: 6 KB of heap per warp -> 4 blocks (32 warps) per SM
 
+// sweeps that can be resident at once with the selected kernel variant (batches larger than this
+// run as several waves of equal duration, so the plan sizes its batches to a multiple of it)
+int eikonal_resident_sweeps() {
+  const bool v1 = getenv("DSURF_EIKONAL_V1") != nullptr, v2 = getenv("DSURF_EIKONAL_V2") != nullptr;
+  const char *gs = getenv("DSURF_EIKONAL_G");
+  const bool g8 = gs && atoi(gs) == 8;
+  int nb = 0;
+  int per_block = kWarpsPerBlock;
+  if (v1) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal<Heap, 1>, kWarpsPerBlock * 32,
+                                                  (size_t)kWarpsPerBlock * 2 * kHeapSm * sizeof(float));
+  } else if (v2) {
+    cudaFuncSetAttribute(k_eikonal<Heap2<kHeapSm2>, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)kWarpsPerBlock * kHeapSm2 * sizeof(int2)));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal<Heap2<kHeapSm2>, 4>, kWarpsPerBlock * 32,
+                                                  (size_t)kWarpsPerBlock * kHeapSm2 * sizeof(int2));
+  } else if (g8) {
+    const size_t sm = (size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2);
+    cudaFuncSetAttribute(k_eikonal3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<8>, kWarpsPerBlock * 32, sm);
+    per_block = kWarpsPerBlock * V3<8>::NG;
+  } else {
+    const size_t sm = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
+    cudaFuncSetAttribute(k_eikonal3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<16>, kWarpsPerBlock * 32, sm);
+    per_block = kWarpsPerBlock * V3<16>::NG;
+  }
+  cudaGetLastError();
+  if (nb < 1) nb = 1;
+  return nb * per_block * sm_count();
+}
+
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
                    const float *d_velv_all, const float *d_risti, BatchView bv, int *launches) {
   if (nsw <= 0) return DSURF_OK;

@@ -307,12 +307,15 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
   const size_t per_slot = Nc * sizeof(int2) + (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) +
                           (size_t)(p->hcap + 1) * 16 + kRefMax * sizeof(float) + sizeof(SweepDesc) +
                           (size_t)maxnrc * (fdm_per_ray + sizeof(RayDesc) + 64);
-  const size_t budget = std::min<size_t>((size_t)(freeb * 0.55), (size_t)64 << 30);
+  const size_t budget = std::min<size_t>((size_t)(freeb * 0.6), (size_t)100 << 30);
   long long nsw_total = 0;
   for (auto &gi : p->gathers) nsw_total += gi.igr == 1 ? 2 : 1;
   long long ms = (long long)(budget / per_slot);
   ms = std::min<long long>(ms, std::max<long long>(nsw_total, 1));
-  ms = std::min<long long>(ms, (long long)sm_count() * 64);
+  {  // batches of at most one resident wave (larger launches would run as equal-length waves)
+    const long long res = eikonal_resident_sweeps();
+    if (res > 0) ms = std::min<long long>(ms, res);
+  }
   ms = std::max<long long>(ms, 1);
   p->maxslots = (int)ms;
   p->maxrays = (int)std::min<long long>((long long)p->maxslots * maxnrc, 1ll << 30);

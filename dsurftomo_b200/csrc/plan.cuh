@@ -82,6 +82,7 @@ struct BatchView {
 int launch_dice(cudaStream_t st, const Geom &g, const double *d_pv_map, float *d_velv, float *d_veln);
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
                    const float *d_velv_all, const float *d_risti, BatchView bv, int *launches);
+int eikonal_resident_sweeps();
 int launch_rays(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, const RayDesc *d_rays, int nrays,
                 const float *d_veln_all, BatchView bv, float *d_tt, float *d_fdm, int4 *d_bbox,
                 int *d_rbint, int *d_err);
