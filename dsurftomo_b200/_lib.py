@@ -87,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "dsurf_plan_set_map", "dsurf_plan_set_dispersion", "dsurf_plan_finalize_dispersion", "dsurf_plan_reset_rows", "dsurf_plan_sweeps", "dsurf_plan_num_gathers",
     "dsurf_plan_num_sweeps", "dsurf_plan_nar", "dsurf_plan_nrows", "dsurf_plan_download",
     "dsurf_plan_debug_sweep", "dsurf_plan_get_dispersion", "dsurf_plan_timings", "dsurf_plan_last_sweeps_ms",
-    "dsurf_lsmr_create", "dsurf_lsmr_create_from_plan", "dsurf_lsmr_destroy", "dsurf_lsmr_set_comm",
+    "dsurf_lsmr_create", "dsurf_lsmr_create_from_plan", "dsurf_lsmr_hint_geometry", "dsurf_lsmr_destroy", "dsurf_lsmr_set_comm",
     "dsurf_lsmr_solve", "dsurf_lsmr_nnz", "dsurf_nccl_unique_id", "dsurf_nccl_comm_init",
     "dsurf_nccl_comm_destroy",
 ]

@@ -314,3 +314,9 @@ class LsmrSystem:
         return dict(x=x, istop=istop.value, itn=itn.value, normA=vals[0].value, condA=vals[1].value,
                     normr=vals[2].value, normAr=vals[3].value, normx=vals[4].value, ms_total=ms[0].value,
                     ms_spmv=ms[1].value, ms_spmtv=ms[2].value)
+
+
+def lsmr_hint_geometry(nx, ny, nz):
+    """Column-order hint for LSMR (columns = k*P + vertex, P=(nx-2)(ny-2), K=nz-1): enables the
+    depth-blocked sparse layout for systems with n == P*K.  CalSurfG/Plan set it automatically."""
+    check(lib().dsurf_lsmr_hint_geometry(C.c_int(nx), C.c_int(ny), C.c_int(nz)), "lsmr_hint_geometry")

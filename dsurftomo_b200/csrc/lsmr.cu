@@ -129,6 +129,205 @@ k_spmv_short(const long long *__restrict__ ptr, const int *__restrict__ idx, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Depth-blocked products.  A sensitivity row touches the same B-spline vertices at every depth
+// (row = S(k,vertex) * fdm(vertex), CalSurfG.f90:1396-1399), so the nz-1 depth columns of one
+// vertex are stored as one block: 1 index + 8 values (36 B for up to 8 non-zeros instead of
+// 8 B each) and the n-vectors are kept internally in the permuted order [vertex][depth] so that a
+// block reads one aligned 32-byte sector of x.  Blocks are built from the caller's COO on the
+// device (build_blocked); entries the reference dropped by its |row| > 1e-4 test are zeros.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dot8(const float4 a0, const float4 a1, const float4 b0, const float4 b1) {
+  double t = (double)a0.x * (double)b0.x;
+  t += (double)a0.y * (double)b0.y;
+  t += (double)a0.z * (double)b0.z;
+  t += (double)a0.w * (double)b0.w;
+  t += (double)a1.x * (double)b1.x;
+  t += (double)a1.y * (double)b1.y;
+  t += (double)a1.z * (double)b1.z;
+  t += (double)a1.w * (double)b1.w;
+  return t;
+}
+
+// y[r] = s*y[r] + sum_blocks val[b][0..7] . x[pos[b]*8 .. +7]      (rows of A; warp per row)
+__global__ void __launch_bounds__(kSpmvWarps * 32)
+k_bspmv_rows(const long long *__restrict__ ptr, const int *__restrict__ pos, const float4 *__restrict__ val,
+             const float4 *__restrict__ x4, float *__restrict__ y, const float *__restrict__ scale_ptr,
+             float scale_sign, const int *__restrict__ rowlist, int nrows, int per_thread,
+             double *__restrict__ partial, const int *__restrict__ stop) {
+  __shared__ double sh[kSpmvWarps * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double sq = 0.0;
+  if (stop == nullptr || *stop == 0) {
+    if (!per_thread) {
+      const int wi = blockIdx.x * kSpmvWarps + w;
+      if (wi < nrows) {
+        const int r = rowlist[wi];
+        const long long b0 = ptr[r], b1 = ptr[r + 1];
+        double acc0 = 0.0, acc1 = 0.0;
+        long long b = b0 + lane;
+        for (; b + 32 < b1; b += 64) {
+          const int pa = pos[b], pb = pos[b + 32];
+          const float4 va0 = val[2 * b], va1 = val[2 * b + 1];
+          const float4 vb0 = val[2 * (b + 32)], vb1 = val[2 * (b + 32) + 1];
+          acc0 += dot8(va0, va1, __ldg(x4 + 2 * (size_t)pa), __ldg(x4 + 2 * (size_t)pa + 1));
+          acc1 += dot8(vb0, vb1, __ldg(x4 + 2 * (size_t)pb), __ldg(x4 + 2 * (size_t)pb + 1));
+        }
+        for (; b < b1; b += 32) {
+          const int pa = pos[b];
+          acc0 += dot8(val[2 * b], val[2 * b + 1], __ldg(x4 + 2 * (size_t)pa), __ldg(x4 + 2 * (size_t)pa + 1));
+        }
+        const double acc = warp_sum(acc0 + acc1);
+        if (lane == 0) {
+          const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
+          const float y0 = scale_ptr ? s * y[r] : 0.0f;
+          const float yn = (float)((double)y0 + acc);
+          y[r] = yn;
+          sq = (double)yn * (double)yn;
+        }
+      }
+    } else {
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t < nrows) {
+        const int r = rowlist[t];
+        double acc = 0.0;
+        for (long long b = ptr[r]; b < ptr[r + 1]; b++) {
+          const int pa = pos[b];
+          acc += dot8(val[2 * b], val[2 * b + 1], __ldg(x4 + 2 * (size_t)pa), __ldg(x4 + 2 * (size_t)pa + 1));
+        }
+        const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
+        const float y0 = scale_ptr ? s * y[r] : 0.0f;
+        const float yn = (float)((double)y0 + acc);
+        y[r] = yn;
+        sq = (double)yn * (double)yn;
+      }
+    }
+  }
+  if (partial) {
+    sh[threadIdx.x] = sq;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+  }
+}
+
+// y[c*8+k] = s*y[c*8+k] + sum_blocks val[b][k] * u[row[b]]   (vertex columns of A; warp per vertex)
+__global__ void __launch_bounds__(kSpmvWarps * 32)
+k_bspmv_cols(const long long *__restrict__ ptr, const int *__restrict__ row, const float4 *__restrict__ val,
+             const float *__restrict__ u, float *__restrict__ y, const float *__restrict__ scale_ptr,
+             float scale_sign, const int *__restrict__ collist, int ncols, int per_thread,
+             double *__restrict__ partial, const int *__restrict__ stop) {
+  __shared__ double sh[kSpmvWarps * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double sq = 0.0;
+  if (stop == nullptr || *stop == 0) {
+    int c = -1;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool writer = false;
+    if (!per_thread) {
+      const int wi = blockIdx.x * kSpmvWarps + w;
+      if (wi < ncols) {
+        c = collist[wi];
+        const long long b0 = ptr[c], b1 = ptr[c + 1];
+        for (long long b = b0 + lane; b < b1; b += 32) {
+          const double uu = (double)__ldg(u + row[b]);
+          const float4 v0 = val[2 * b], v1 = val[2 * b + 1];
+          a[0] += (double)v0.x * uu; a[1] += (double)v0.y * uu; a[2] += (double)v0.z * uu; a[3] += (double)v0.w * uu;
+          a[4] += (double)v1.x * uu; a[5] += (double)v1.y * uu; a[6] += (double)v1.z * uu; a[7] += (double)v1.w * uu;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = warp_sum(a[k]);
+        writer = lane == 0;
+      }
+    } else {
+      const int t = blockIdx.x * blockDim.x + threadIdx.x;
+      if (t < ncols) {
+        c = collist[t];
+        for (long long b = ptr[c]; b < ptr[c + 1]; b++) {
+          const double uu = (double)__ldg(u + row[b]);
+          const float4 v0 = val[2 * b], v1 = val[2 * b + 1];
+          a[0] += (double)v0.x * uu; a[1] += (double)v0.y * uu; a[2] += (double)v0.z * uu; a[3] += (double)v0.w * uu;
+          a[4] += (double)v1.x * uu; a[5] += (double)v1.y * uu; a[6] += (double)v1.z * uu; a[7] += (double)v1.w * uu;
+        }
+        writer = true;
+      }
+    }
+    if (writer) {
+      const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float y0 = scale_ptr ? s * y[(size_t)c * 8 + k] : 0.0f;
+        const float yn = (float)((double)y0 + a[k]);
+        y[(size_t)c * 8 + k] = yn;
+        sq += (double)yn * (double)yn;
+      }
+    }
+  }
+  if (partial) {
+    sh[threadIdx.x] = sq;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+  }
+}
+
+// build helpers
+__global__ void k_blk_keys(const int *__restrict__ rows1, const int *__restrict__ cols1, long long nnz, int P,
+                           long long M, int by_rows, unsigned long long *__restrict__ keys, int *__restrict__ perm) {
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz; i += tot) {
+    const long long r = rows1[i] - 1, c = cols1[i] - 1;
+    const long long pos0 = c % P;
+    keys[i] = by_rows ? (unsigned long long)(r * (long long)P + pos0) : (unsigned long long)(pos0 * M + r);
+    perm[i] = (int)i;
+  }
+}
+__global__ void k_blk_heads(const unsigned long long *__restrict__ keys, long long nnz, int *__restrict__ head) {
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz; i += tot)
+    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+__global__ void k_blk_fill(const unsigned long long *__restrict__ keys, const int *__restrict__ perm,
+                           const long long *__restrict__ bid_incl, const int *__restrict__ cols1,
+                           const float *__restrict__ vals, long long nnz, int P, long long M, int by_rows,
+                           int *__restrict__ bidx, float *__restrict__ bval, int *__restrict__ cnt) {
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz; i += tot) {
+    const long long b = bid_incl[i] - 1;
+    const unsigned long long key = keys[i];
+    const int src = perm[i];
+    const int k = (cols1[src] - 1) / P;
+    // duplicates (same row, same column) add up like in the reference's aprod
+    atomicAdd(bval + b * 8 + k, vals[src]);
+    if (i == 0 || keys[i - 1] != key) {
+      long long outer, inner;
+      if (by_rows) {
+        outer = (long long)(key / (unsigned long long)P);
+        inner = (long long)(key % (unsigned long long)P);
+      } else {
+        outer = (long long)(key / (unsigned long long)M);
+        inner = (long long)(key % (unsigned long long)M);
+      }
+      bidx[b] = (int)inner;
+      atomicAdd(cnt + outer, 1);
+    }
+  }
+}
+// x (reference order k*P+pos) <-> internal order pos*8+k
+__global__ void k_unpermute(const float *__restrict__ xin, float *__restrict__ xout, int P, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P * K) {
+    const int k = i / P, pos = i % P;
+    xout[i] = xin[(size_t)pos * 8 + k];
+  }
+}
+
 // one-block deterministic reduction of `np` partials (fixed strided order + tree)
 __device__ double block_reduce_partials(const double *partial, int np) {
   __shared__ double sh[1024];
@@ -565,6 +764,8 @@ struct Compressed {
   DevBuf<float> val;
   DevBuf<int> longl, shortl;
   int nrows = 0, nlong = 0, nshort = 0;
+  int kind = 0;  // 0 scalar CSR/CSC, 1 depth-blocked rows, 2 depth-blocked vertex columns
+  long long nblk = 0;
   int blocks() const { return (nlong + kSpmvWarps - 1) / kSpmvWarps + (nshort + 255) / 256; }
 };
 
@@ -574,6 +775,9 @@ struct dsurf_lsmr_sys {
   cudaStream_t st = nullptr;
   bool own_stream = false;
   Compressed A, At;  // A: rows of A (u += A v); At: columns of A (v += A'u)
+  int P = 0, K = 0;  // depth-blocked layout (P vertices x K depths) when K > 0
+  int n_int = 0;     // length of the n-vectors in the internal layout (P*8 when blocked)
+  DevBuf<float> xout;
   DevBuf<float> b, u, v, h, hbar, x, localV;
   DevBuf<double> partial, partial2;
   DevBuf<LsmrScalars> S;
@@ -613,10 +817,87 @@ static int classify_rows(cudaStream_t st, Compressed &C, int nrows) {
   return DSURF_OK;
 }
 
+// geometry hint for the depth-blocked layout: set by dsurf_plan_create / dsurf_lsmr_hint_geometry
+static int g_hint_P = 0, g_hint_K = 0;
+
+// Builds the depth-blocked structure of A (by_rows) or A' (vertex columns) from device COO.
+static int build_blocked(cudaStream_t st, const int *rows1, const int *cols1, const float *vals, long long nnz,
+                         int m, int P, bool by_rows, Compressed &C) {
+  const int nouter = by_rows ? m : P;
+  DevBuf<unsigned long long> k_in, k_out;
+  DevBuf<int> p_in, p_out, head, cnt;
+  DevBuf<long long> bid, wide, scan;
+  DevBuf<char> tmp;
+  const size_t nn = nnz > 0 ? (size_t)nnz : 1;
+  if (k_in.reserve(nn) || k_out.reserve(nn) || p_in.reserve(nn) || p_out.reserve(nn) || head.reserve(nn) ||
+      bid.reserve(nn) || cnt.reserve(nouter + 1) || wide.reserve(nouter + 1) || scan.reserve(nouter + 1) ||
+      C.ptr.reserve(nouter + 1)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (blocked build)");
+    return DSURF_ERR_CUDA;
+  }
+  k_blk_keys<<<grid_for(nnz), 256, 0, st>>>(rows1, cols1, nnz, P, (long long)m, by_rows ? 1 : 0, k_in.p, p_in.p);
+  int end_bit = 1;
+  const unsigned long long maxkey = (unsigned long long)(by_rows ? (long long)m * P : (long long)P * m);
+  while ((1ull << end_bit) <= maxkey && end_bit < 63) end_bit++;
+  size_t sb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sb, k_in.p, k_out.p, p_in.p, p_out.p, nnz, 0, end_bit, st);
+  if (tmp.reserve(sb + 16)) return DSURF_ERR_CUDA;
+  cub::DeviceRadixSort::SortPairs(tmp.p, sb, k_in.p, k_out.p, p_in.p, p_out.p, nnz, 0, end_bit, st);
+  k_blk_heads<<<grid_for(nnz), 256, 0, st>>>(k_out.p, nnz, head.p);
+  size_t tb = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tb, head.p, bid.p, nnz, st);
+  if (tmp.reserve(tb + 16)) return DSURF_ERR_CUDA;
+  cub::DeviceScan::InclusiveSum(tmp.p, tb, head.p, bid.p, nnz, st);
+  long long nblk = 0;
+  if (nnz > 0) DS_CUDA(cudaMemcpyAsync(&nblk, bid.p + (nnz - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  C.nblk = nblk;
+  const size_t nb = nblk > 0 ? (size_t)nblk : 1;
+  if (C.idx.reserve(nb) || C.val.reserve(nb * 8)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (blocks)");
+    return DSURF_ERR_CUDA;
+  }
+  DS_CUDA(cudaMemsetAsync(C.val.p, 0, nb * 8 * sizeof(float), st));
+  DS_CUDA(cudaMemsetAsync(cnt.p, 0, (nouter + 1) * sizeof(int), st));
+  if (nnz > 0)
+    k_blk_fill<<<grid_for(nnz), 256, 0, st>>>(k_out.p, p_out.p, bid.p, cols1, vals, nnz, P, (long long)m,
+                                             by_rows ? 1 : 0, C.idx.p, C.val.p, cnt.p);
+  k_widen<<<grid_for(nouter + 1), 256, 0, st>>>(cnt.p, wide.p, nouter + 1);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, wide.p, scan.p, nouter + 1, st);
+  if (tmp.reserve(tb + 16)) return DSURF_ERR_CUDA;
+  cub::DeviceScan::ExclusiveSum(tmp.p, tb, wide.p, scan.p, nouter + 1, st);
+  k_to_ptr<<<grid_for(nouter + 1), 256, 0, st>>>(cnt.p, scan.p, nouter, nblk, C.ptr.p);
+  DS_CUDA(cudaStreamSynchronize(st));
+  DS_CUDA(cudaGetLastError());
+  C.kind = by_rows ? 1 : 2;
+  return DSURF_OK;
+}
+
 // y = s*y + C x (all rows); partial (may be null) receives C.blocks() block sums of y^2
 static void launch_product(cudaStream_t st, const Compressed &C, const float *x, float *y, const float *scale_ptr,
                            float sign, double *partial, const int *stop) {
   const int ga = (C.nlong + kSpmvWarps - 1) / kSpmvWarps;
+  if (C.kind == 1 || C.kind == 2) {
+    const float4 *v4 = reinterpret_cast<const float4 *>(C.val.p);
+    const int gb = (C.nshort + 255) / 256;
+    if (C.kind == 1) {
+      const float4 *x4 = reinterpret_cast<const float4 *>(x);
+      if (C.nlong > 0)
+        k_bspmv_rows<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
+                                                     partial, stop);
+      if (C.nshort > 0)
+        k_bspmv_rows<<<gb, 256, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.shortl.p, C.nshort, 1,
+                                         partial ? partial + ga : nullptr, stop);
+    } else {
+      if (C.nlong > 0)
+        k_bspmv_cols<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
+                                                     partial, stop);
+      if (C.nshort > 0)
+        k_bspmv_cols<<<gb, 256, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.shortl.p, C.nshort, 1,
+                                         partial ? partial + ga : nullptr, stop);
+    }
+    return;
+  }
   if (C.nlong > 0)
     k_spmv_warp<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, C.val.p, x, y, scale_ptr, sign, C.longl.p, C.nlong,
                                                 partial, stop);
@@ -639,19 +920,34 @@ int lsmr_sys_create_dev(dsurf_lsmr_sys **out, int m, int n, long long nnz, const
   s->own_stream = true;
   cudaStream_t st = s->st;
   cudaDeviceSynchronize();  // inputs were uploaded on the legacy default stream
-  int rc = build_compressed(st, d_rows1, d_cols1, d_vals, nnz, m, s->A.ptr, s->A.idx, s->A.val);
-  if (rc == DSURF_OK) rc = build_compressed(st, d_cols1, d_rows1, d_vals, nnz, n, s->At.ptr, s->At.idx, s->At.val);
-  if (rc == DSURF_OK) rc = classify_rows(st, s->A, m);
-  if (rc == DSURF_OK) rc = classify_rows(st, s->At, n);
+  int rc = DSURF_OK;
+  const bool blocked = g_hint_K >= 2 && g_hint_K <= 8 && (long long)g_hint_P * g_hint_K == n &&
+                       getenv("DSURF_LSMR_NO_BLOCK") == nullptr;
+  s->n_int = n;
+  if (blocked) {
+    s->P = g_hint_P;
+    s->K = g_hint_K;
+    s->n_int = g_hint_P * 8;
+    rc = build_blocked(st, d_rows1, d_cols1, d_vals, nnz, m, s->P, true, s->A);
+    if (rc == DSURF_OK) rc = build_blocked(st, d_rows1, d_cols1, d_vals, nnz, m, s->P, false, s->At);
+    if (rc == DSURF_OK) rc = classify_rows(st, s->A, m);
+    if (rc == DSURF_OK) rc = classify_rows(st, s->At, s->P);
+  } else {
+    rc = build_compressed(st, d_rows1, d_cols1, d_vals, nnz, m, s->A.ptr, s->A.idx, s->A.val);
+    if (rc == DSURF_OK) rc = build_compressed(st, d_cols1, d_rows1, d_vals, nnz, n, s->At.ptr, s->At.idx, s->At.val);
+    if (rc == DSURF_OK) rc = classify_rows(st, s->A, m);
+    if (rc == DSURF_OK) rc = classify_rows(st, s->At, n);
+  }
   if (rc != DSURF_OK) {
     delete s;
     return rc;
   }
   const int np = std::max(std::max(s->A.blocks(), s->At.blocks()), 4096) + 16;
   s->np_cap = np;
-  if (s->b.reserve(m) || s->u.reserve(m) || s->v.reserve(n) || s->h.reserve(n) || s->hbar.reserve(n) ||
-      s->x.reserve(n) || s->partial.reserve(np) || s->partial2.reserve(np) || s->S.reserve(1) ||
-      s->vpart.reserve(n + 8) || s->red.reserve(8)) {
+  const size_t ni = (size_t)s->n_int;
+  if (s->b.reserve(m) || s->u.reserve(m) || s->v.reserve(ni) || s->h.reserve(ni) || s->hbar.reserve(ni) ||
+      s->x.reserve(ni) || s->xout.reserve(ni) || s->partial.reserve(np) || s->partial2.reserve(np) ||
+      s->S.reserve(1) || s->vpart.reserve(ni + 8) || s->red.reserve(8)) {
     set_error(__FILE__, __LINE__, "cudaMalloc failed (lsmr vectors)");
     delete s;
     return DSURF_ERR_CUDA;
@@ -681,6 +977,15 @@ extern "C" int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar
   return lsmr_sys_create_dev(sys, m, n, nar, dr.p, dc.p, dv.p, db.p);
 }
 
+// Tells the solver that columns are ordered k*P + vertex with P = (nx-2)(ny-2) vertices and
+// K = nz-1 depths (main.f90:289, CalSurfG.f90:1400), which enables the depth-blocked layout for
+// systems with n == P*K.  Called by dsurf_plan_create (i.e. by every CalSurfG call).
+extern "C" int dsurf_lsmr_hint_geometry(int nx, int ny, int nz) {
+  g_hint_P = (nx - 2) * (ny - 2);
+  g_hint_K = nz - 1;
+  return DSURF_OK;
+}
+
 extern "C" int dsurf_lsmr_destroy(dsurf_lsmr_sys *sys) {
   delete sys;
   return DSURF_OK;
@@ -698,7 +1003,7 @@ extern "C" int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *comm, int rank, in
 static int enqueue_iteration(dsurf_lsmr_sys *s, float damp, float atol, float btol, float ctol, int itnlim,
                              int force_iters, int localVecs, bool dist) {
   cudaStream_t st = s->st;
-  const int m = s->m, n = s->n;
+  const int m = s->m, n = s->n_int;  // n-vectors in the internal layout
   LsmrScalars *S = s->S.p;
   double *part = s->partial.p, *part2 = s->partial2.p;
   const int gvec = std::min(std::max((n + 255) / 256, 1), sm_count() * 4);
@@ -735,8 +1040,8 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   if (!s) return DSURF_ERR_BAD_ARG;
   DS_CHECK(ensure_device());
   cudaStream_t st = s->st;
-  const int m = s->m, n = s->n;
-  const int localVecs = std::min(localSize, std::min(m, n));
+  const int m = s->m, n = s->n_int;  // n-vectors in the internal layout
+  const int localVecs = std::min(localSize, std::min(m, s->n));
   if (localVecs > 0 && s->localV.reserve((size_t)n * localVecs)) {
     set_error(__FILE__, __LINE__, "cudaMalloc failed (localV)");
     return DSURF_ERR_CUDA;
@@ -817,7 +1122,14 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   cudaEventRecord(e1, st);
   LsmrScalars hs;
   DS_CUDA(cudaMemcpyAsync(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost, st));
-  if (x_host) DS_CUDA(cudaMemcpyAsync(x_host, s->x.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (x_host) {
+    const float *xsrc = s->x.p;
+    if (s->K > 0) {  // back to the reference's column order k*P + pos
+      k_unpermute<<<(s->n + 255) / 256, 256, 0, st>>>(s->x.p, s->xout.p, s->P, s->K);
+      xsrc = s->xout.p;
+    }
+    DS_CUDA(cudaMemcpyAsync(x_host, xsrc, (size_t)s->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
   DS_CUDA(cudaStreamSynchronize(st));
   DS_CUDA(cudaGetLastError());
   if (gexec) cudaGraphExecDestroy(gexec);

@@ -171,6 +171,7 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
                                  int kmax, int nsrcsurf, int nrcf) {
   DS_CHECK(ensure_device());
   if (!out || nx < 4 || ny < 4 || nz < 2 || kmax != kmaxRc + kmaxRg + kmaxLc + kmaxLg) return DSURF_ERR_BAD_ARG;
+  dsurf_lsmr_hint_geometry(nx, ny, nz);
   auto *p = new dsurf_plan();
   make_geom(p->g, nx, ny, goxdf, gozdf, dvxdf, dvzdf);
   p->nz = nz;

@@ -179,6 +179,9 @@ int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar, const int
 /* same, taking the COO a plan holds in HBM plus device-side host glue (main.f90:361-466) */
 int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **sys, dsurf_plan *plan, const float *obst,
                                 float threshold0, float weight);
+/* column-order hint (P = (nx-2)(ny-2) vertices, K = nz-1 depths) enabling the depth-blocked
+ * sparse layout when n == P*K; set automatically by every dsurf_plan_create / CalSurfG call */
+int dsurf_lsmr_hint_geometry(int nx, int ny, int nz);
 int dsurf_lsmr_destroy(dsurf_lsmr_sys *sys);
 /* multi-GPU: rows are partitioned over ranks; comm is an ncclComm_t created by the host side
  * (see dsurftomo_b200/dist.py); the per-iteration exchange is one all-reduce of n+1 floats. */
