@@ -302,6 +302,7 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
   p->hcap = 8 * (p->g.nnx + p->g.nnz) + 1024;
+  if (const char *hc = getenv("DSURF_HCAP")) p->hcap = std::max(16, atoi(hc));  // test hook: force heap-slab growth
   const size_t fdm_per_ray = (size_t)(p->g.nvz + 2) * (p->g.nvx + 2) * sizeof(float);
   int maxnrc = 1;
   for (auto &gi : p->gathers) maxnrc = std::max(maxnrc, gi.nrc);

@@ -299,3 +299,78 @@ def test_lsmr_blocked_layout_matches_scalar_layout(taipei):
     assert np.abs(g1["x"] - xs).max() <= 2e-4 * np.abs(xs).max()
     assert np.abs(g2["x"] - xs).max() <= 2e-4 * np.abs(xs).max()
     api.lsmr_hint_geometry(pb.nx, pb.ny, pb.nz)
+
+
+def test_heap_slab_growth_path_is_exact():
+    """A deliberately tiny narrow-band slab (DSURF_HCAP) must trigger the grow-and-retry path and
+    still reproduce the oracle bit for bit."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, DSURF_HCAP="600")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "sweep_bit_exact"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ BASELINE sizes (cfg 3 grid)
+@pytest.fixture(scope="module")
+def cfg3_slice():
+    """The 1025 x 1025 propagation grid of BASELINE configs[2] with one period and a few gathers."""
+    pb = inputs.synthetic_problem(131, 1, 6, ("Rc",), nrecv=5, name="cfg3_grid_slice")
+    pv4, sen12 = inputs.synthetic_dispersion(pb)
+    return pb, pv4, sen12
+
+
+def test_full_size_grid_sweep_bit_exact(cfg3_slice):
+    pb, pv4, sen12 = cfg3_slice
+    plan = api.Plan(pb)
+    plan.set_dispersion(0, pv4[0], *sen12[0:3])
+    plan.finalize_dispersion()
+    g = 3
+    got = plan.debug_sweep(g, 1)
+    ref = O.fmm_sweep(pb.nx, pb.ny, pb.goxd, pb.gozd, pb.dvxd, pb.dvzd, pv4[0][0], pb.scxf[0, g], pb.sczf[0, g])
+    assert ref["err"] == 0 and got["ttn"].shape == (1025, 1025)
+    assert np.array_equal(_bits(got["veln"]), _bits(ref["veln"]))
+    assert np.array_equal(_bits(got["ttn"]), _bits(ref["ttn"]))
+    nrc = int(pb.nrc1[0, g])
+    err, tt, fdm = O.sweep_rays(pb.nx, pb.ny, pb.goxd, pb.gozd, pb.dvxd, pb.dvzd, pv4[0][0], pb.scxf[0, g],
+                                pb.sczf[0, g], pb.rcxf[0, g, :nrc], pb.rczf[0, g, :nrc])
+    assert err == 0
+    assert np.array_equal(_bits(got["fdm"][:nrc]), _bits(fdm))
+    # size-independent properties of the travel-time field
+    t = got["ttn"]
+    assert np.isfinite(t).all() and t.min() >= 0.0
+    dx = np.abs(np.diff(t, axis=0)).max()
+    dz = np.abs(np.diff(t, axis=1)).max()
+    vmin = got["veln"].min()
+    h = 6371.0 * np.deg2rad(pb.dvxd) / 8
+    assert max(dx, dz) <= 1.5 * h / vmin  # |grad T| = 1/v: neighbours differ by at most ~h/v
+    plan.close()
+
+
+def test_full_size_rows_match_oracle_and_normal_equations(cfg3_slice):
+    pb, pv4, sen12 = cfg3_slice
+    plan = api.Plan(pb)
+    plan.set_dispersion(0, pv4[0], *sen12[0:3])
+    plan.finalize_dispersion()
+    plan.reset_rows()
+    plan.sweeps()
+    got = plan.download()
+    ref = O.calsurfg_pre(pb, pv4, sen12, nthreads=8, maxnar=4_000_000)
+    assert ref["err"] == 0 and got["nar"] == ref["nar"]
+    assert np.array_equal(got["row"], ref["row"]) and np.array_equal(got["col"], ref["col"])
+    assert np.array_equal(_bits(got["rw"]), _bits(ref["rw"])) and np.array_equal(_bits(got["dsurf"]), _bits(ref["dsurf"]))
+    # LSMR at n = 133 128 unknowns: the damped normal equations are satisfied
+    s = hostglue.host_glue(pb, got["dsurf"], got["row"], got["col"], got["rw"])
+    iw = hostglue.pack_iw(s["rows"], s["cols"])
+    sol = api.LSMR(s["m"], s["n"], len(iw), len(s["vals"]), iw, s["vals"], s["cbst"], pb.damp, 1e-6, 1e-6, 100.0, 400, 10)
+    import scipy.sparse as sp
+
+    A = sp.coo_matrix((s["vals"].astype(np.float64), (s["rows"] - 1, s["cols"] - 1)), shape=(s["m"], s["n"])).tocsr()
+    x = sol["x"].astype(np.float64)
+    g = A.T @ (A @ x - s["cbst"].astype(np.float64)) + pb.damp ** 2 * x
+    assert np.linalg.norm(g) <= 1e-4 * np.linalg.norm(A.T @ s["cbst"].astype(np.float64))
+    plan.close()
