@@ -13,7 +13,7 @@ from dsurftomo_b200 import _lib, api, inputs
 def _header_symbols():
     txt = open(os.path.join(ROOT, "include", "dsurftomo_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    names = re.findall(r"\b(?:int|void|int64_t|const char \*)\s*\*?\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(", txt)
+    names = re.findall(r"\b(?:int|void|int64_t|double|float|const char \*)\s*\*?\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(", txt)
     return sorted(set(n for n in names if n.startswith(("dsurf_", "__lsmr")) or n.endswith("_")))
 
 
