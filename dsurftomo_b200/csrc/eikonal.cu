@@ -106,6 +106,12 @@ struct Grid {
   const float *risti;  // earth*sin(gox+(ix-1)*dnx), [nnx]
   int nnx, nnz;
   float dnx, dnz, earth;
+  unsigned mdiv;  // n / nnz == __umulhi(n, mdiv) >> sdiv for 0 <= n < 2^31 (nnz = 8k+1 is never a power of two)
+  int sdiv;
+  __device__ __forceinline__ void set_div() {
+    sdiv = 31 - __clz(nnz);
+    mdiv = (unsigned)((1ull << (32 + sdiv)) / (unsigned)nnz) + 1u;
+  }
 };
 
 // sift-up from position tpc with (key,node): addtree (:768-805) / updtree (:894-921)
@@ -767,6 +773,7 @@ k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__
   R.dnx = g.drnx;
   R.dnz = g.drnz;
   R.earth = g.earth;
+  R.set_div();
   int ntr = 0;
   {
     const int isx = d.tsx, isz = d.tsz;
@@ -843,6 +850,7 @@ k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__
   C.dnx = g.dnx;
   C.dnz = g.dnz;
   C.earth = g.earth;
+  C.set_div();
   ntr = 0;
   for (int cx = 0; cx < bw; cx++) {
     for (int base = 0; base < bh; base += 32) {
@@ -914,7 +922,8 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
     if (!active) continue;
     do {
     const int root = H.sm[1].y;
-    const int ix = root / nnz + 1, iz = root - (ix - 1) * nnz + 1;
+    const int ixm = (int)(__umulhi((unsigned)root, G.mdiv) >> G.sdiv);  // root / nnz (exact, see Grid::set_div)
+    const int ix = ixm + 1, iz = root - ixm * nnz + 1;
     if (REFINED) {
       int swrg = 0;
       if (ix == 1 && vnl != 1) swrg = 1;
@@ -963,13 +972,11 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
         if (xin && sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz) sn[j] = G.node[(sx - 1) * nnz + (sz - 1)];
       }
     }
-    int xm0 = -1, xm1 = -1, xm2 = -1, xm3 = -1;
-#define TRACK_MOVE(nid, newpos)        \
-  {                                    \
-    if ((nid) == xid0) xm0 = (newpos); \
-    if ((nid) == xid1) xm1 = (newpos); \
-    if ((nid) == xid2) xm2 = (newpos); \
-    if ((nid) == xid3) xm3 = (newpos); \
+    // heap slot of this lane's own neighbour if the pop moves it (node ids are never -1)
+    int xmown = -1;
+#define TRACK_MOVE(nid, newpos) \
+  {                             \
+    if ((nid) == oidx) xmown = (newpos); \
   }
     // ---- (2) downtree (:816-885)
     if (ntr == 1) {
@@ -1098,15 +1105,14 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
     for (int g = 0; g < 4; g++) {
       pr[g] = __shfl_sync(gm, proc, gbase + LPX * g);
       tv[g] = __shfl_sync(gm, trav, gbase + LPX * g);
-      const int st = __shfl_sync(gm, xn.y, gbase + LPX * g);
+      const int st = __shfl_sync(gm, (xmown >= 0) ? xmown : xn.y, gbase + LPX * g);
       xi[g] = (g == 0) ? xid0 : (g == 1) ? xid1 : (g == 2) ? xid2 : xid3;
-      const int xm = (g == 0) ? xm0 : (g == 1) ? xm1 : (g == 2) ? xm2 : xm3;
       ppos[g] = 0;
       if (pr[g] == 1) {
         nfar++;
         ppos[g] = ntr + nfar;
       } else if (pr[g] == 2) {
-        ppos[g] = (xm >= 0) ? xm : st;
+        ppos[g] = st;
       }
     }
     const int mypos = (Xown == 0) ? ppos[0] : (Xown == 1) ? ppos[1] : (Xown == 2) ? ppos[2] : ppos[3];
@@ -1131,7 +1137,6 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
       if (!pr[g]) continue;
       const int xg = xi[g];
       const float tvg = tv[g];
-      G.node[xg].x = __float_as_int(tvg);
       int tpc;
       if (pr[g] == 1) {
         ntr = ntr + 1;
@@ -1167,7 +1172,7 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
       }
       const int2 ne = make_int2(__float_as_int(tvg), xg);
       H.set(tpc, ne);
-      G.node[xg].y = tpc;
+      G.node[xg] = make_int2(__float_as_int(tvg), tpc);  // trial time + heap slot in one 8-byte store
       if (moved) {
         slow = true;
       } else {
@@ -1267,6 +1272,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
   R.dnx = g.drnx;
   R.dnz = g.drnz;
   R.earth = g.earth;
+  R.set_div();
   int ntr = 0;
   {
     const int isx = d.tsx, isz = d.tsz;
@@ -1335,6 +1341,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
   C.dnx = g.dnx;
   C.dnz = g.dnz;
   C.earth = g.earth;
+  C.set_div();
   ntr = 0;
   for (int cx = 0; cx < bw; cx++) {
     for (int base = 0; base < bh; base += kG) {
