@@ -79,14 +79,15 @@ def ptr(a, ct):
 
 EXPORTED_SYMBOLS = [
     # gfortran-convention drop-ins
-    "calsurfg_", "depthkernel_", "caldespersion_", "surfdisp96_", "__lsmrmodule_MOD_lsmr", "aprod_",
+    "calsurfg_", "depthkernel_", "caldespersion_", "surfdisp96_", "__lsmrmodule_MOD_lsmr", "aprod_", "synthetic_",
     # neutral C API
-    "dsurf_last_error", "dsurf_set_device", "dsurf_build_info", "dsurf_calsurfg", "dsurf_depthkernel",
+    "dsurf_last_error", "dsurf_set_device", "dsurf_build_info", "dsurf_calsurfg", "dsurf_synthetic", "dsurf_depthkernel",
     "dsurf_surfdisp96", "dsurf_surfdisp96_batch", "dsurf_lsmr", "dsurf_aprod",
-    "dsurf_plan_create", "dsurf_plan_destroy", "dsurf_plan_set_model", "dsurf_plan_dispersion",
+    "dsurf_plan_create", "dsurf_plan_create_forward", "dsurf_plan_destroy", "dsurf_plan_set_model", "dsurf_plan_dispersion",
     "dsurf_plan_set_map", "dsurf_plan_set_dispersion", "dsurf_plan_finalize_dispersion", "dsurf_plan_reset_rows", "dsurf_plan_sweeps", "dsurf_plan_num_gathers",
     "dsurf_plan_num_sweeps", "dsurf_plan_nar", "dsurf_plan_nrows", "dsurf_plan_download",
     "dsurf_plan_debug_sweep", "dsurf_plan_get_dispersion", "dsurf_plan_timings", "dsurf_plan_last_sweeps_ms",
+    "dsurf_plan_glue_results", "dsurf_plan_update_model",
     "dsurf_lsmr_create", "dsurf_lsmr_create_from_plan", "dsurf_lsmr_hint_geometry", "dsurf_lsmr_destroy", "dsurf_lsmr_set_comm",
     "dsurf_lsmr_solve", "dsurf_lsmr_nnz", "dsurf_nccl_unique_id", "dsurf_nccl_comm_init",
     "dsurf_nccl_comm_destroy",

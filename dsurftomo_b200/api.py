@@ -131,6 +131,25 @@ def CalSurfG(pb, vels=None, maxnar=None):
                 rbint=rbint.value)
 
 
+def synthetic(pb, vels=None, noiselevel=0.0, outdir=None, seed=20150131):
+    """subroutine synthetic (CalSurfG.f90:2412-2865): forward times through `vels` (the "true"
+    model) on the gd = 5 propagation grid; returns obst (dall,) and the boundary-ray flag."""
+    k = _plan_args(pb, vels)
+    obst = np.zeros(max(pb.dall, 1), F32)
+    rb = C.c_int(0)
+    check(lib().dsurf_synthetic(
+        C.c_int(pb.nx), C.c_int(pb.ny), C.c_int(pb.nz), C.c_int(pb.maxvp), ptr(k["vels"], C.c_float),
+        ptr(obst, C.c_float), C.c_float(pb.goxd), C.c_float(pb.gozd), C.c_float(pb.dvxd), C.c_float(pb.dvzd),
+        C.c_int(pb.kmaxRc), C.c_int(pb.kmaxRg), C.c_int(pb.kmaxLc), C.c_int(pb.kmaxLg),
+        ptr(k["tRc"], C.c_double), ptr(k["tRg"], C.c_double), ptr(k["tLc"], C.c_double), ptr(k["tLg"], C.c_double),
+        ptr(k["wavetype"], C.c_int), ptr(k["igrt"], C.c_int), ptr(k["periods"], C.c_int), ptr(k["depz"], C.c_float),
+        C.c_float(pb.minthk), ptr(k["scxf"], C.c_float), ptr(k["sczf"], C.c_float), ptr(k["rcxf"], C.c_float),
+        ptr(k["rczf"], C.c_float), ptr(k["nrc1"], C.c_int), ptr(k["nsrc1"], C.c_int), C.c_int(pb.kmax),
+        C.c_int(pb.nsrc), C.c_int(pb.nrc), C.c_float(noiselevel),
+        C.c_char_p(outdir.encode()) if outdir is not None else None, C.c_uint64(seed), C.byref(rb)), "synthetic")
+    return dict(obst=obst[: pb.dall], rbint=rb.value)
+
+
 def aprod(mode, m, n, x, y, leniw, lenrw, iw, rw):
     """aprod.f90:7 -- mode 1: y += A x; mode 2: x += A' y.  Returns (x, y)."""
     x = _c(x, F32).copy()
@@ -162,11 +181,14 @@ def LSMR(m, n, leniw, lenrw, iw, rw, b, damp, atol, btol, conlim, itnlim, localS
 class Plan:
     """Device-resident forward/sensitivity plan (the kernels CalSurfG runs, staged)."""
 
-    def __init__(self, pb, vels=None):
+    def __init__(self, pb, vels=None, forward=False):
+        """forward=True: the forward-only plan of subroutine synthetic (gd = 5, times only)."""
         self.pb = pb
+        self.forward = forward
         k = self._keep = _plan_args(pb, vels)
         h = C.c_void_p()
-        check(lib().dsurf_plan_create(
+        create = lib().dsurf_plan_create_forward if forward else lib().dsurf_plan_create
+        check(create(
             C.byref(h), C.c_int(pb.nx), C.c_int(pb.ny), C.c_int(pb.nz), ptr(k["vels"], C.c_float),
             C.c_float(pb.goxd), C.c_float(pb.gozd), C.c_float(pb.dvxd), C.c_float(pb.dvzd),
             C.c_int(pb.kmaxRc), C.c_int(pb.kmaxRg), C.c_int(pb.kmaxLc), C.c_int(pb.kmaxLg),
@@ -205,7 +227,7 @@ class Plan:
 
     def set_dispersion(self, type_, pv, sen_vs, sen_vp, sen_rho):
         """Caller-provided dispersion results of one data type (0 Rc, 1 Rg, 2 Lc, 3 Lg)."""
-        arrs = [_c(a, F64) for a in (pv, sen_vs, sen_vp, sen_rho)]
+        arrs = [_c(a, F64) if a is not None else None for a in (pv, sen_vs, sen_vp, sen_rho)]
         check(lib().dsurf_plan_set_dispersion(self.h, C.c_int(type_), *[ptr(a, C.c_double) for a in arrs]),
               "plan_set_dispersion")
 
@@ -241,6 +263,29 @@ class Plan:
                                         ptr(dsurf, C.c_float), C.byref(rb)), "plan_download")
         return dict(nar=n, row=rows[:n], rw=rw[:n], col=col[:n], dsurf=dsurf[: self.pb.dall], rbint=rb.value)
 
+    def glue_results(self, want_vectors=True):
+        """cbst / datweight / statistics left by LsmrSystem.from_plan (main.f90:361-394)."""
+        dall = self.pb.dall
+        cb = np.zeros(dall, F32) if want_vectors else None
+        dw = np.zeros(dall, F32) if want_vectors else None
+        st = np.zeros(4, F32)
+        m, nar = C.c_int(0), C.c_int64(0)
+        check(lib().dsurf_plan_glue_results(self.h, ptr(cb, C.c_float), ptr(dw, C.c_float), ptr(st, C.c_float),
+                                            C.byref(m), C.byref(nar)), "plan_glue_results")
+        return dict(cbst=cb, datweight=dw, q25=float(st[0]), q75=float(st[1]), maxnorm=float(st[2]),
+                    averdws=float(st[3]), m=m.value, nar=nar.value)
+
+    def update_model(self, lsmr_system, minvel=None, maxvel=None):
+        """main.f90:518-532 on the device; returns (updated model [nz][ny][nx], clipped dv)."""
+        pb = self.pb
+        dv = np.zeros(pb.maxvp, F32)
+        vs = np.zeros((pb.nz, pb.ny, pb.nx), F32)
+        check(lib().dsurf_plan_update_model(
+            self.h, lsmr_system.h, C.c_float(pb.minvel if minvel is None else minvel),
+            C.c_float(pb.maxvel if maxvel is None else maxvel), ptr(dv, C.c_float), ptr(vs, C.c_float)),
+            "plan_update_model")
+        return vs, dv
+
     def timings(self):
         ms = np.zeros(8, F64)
         check(lib().dsurf_plan_timings(self.h, ptr(ms, C.c_double)), "plan_timings")
@@ -252,7 +297,7 @@ class Plan:
         pb = self.pb
         ncol = pb.nx * pb.ny
         kt = (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)[type_]
-        pvcols = pb.kmax if type_ in (0, 2) else max(kt, 1)
+        pvcols = pb.kmax if (type_ in (0, 2) and not self.forward) else max(kt, 1)
         pv = np.zeros((pvcols, ncol), F64)
         sen = [np.zeros((pb.nz, max(kt, 1), ncol), F64) for _ in range(3)]
         check(lib().dsurf_plan_get_dispersion(self.h, C.c_int(type_), ptr(pv, C.c_double),
@@ -288,6 +333,21 @@ class LsmrSystem:
                                       ptr(rows1, C.c_int), ptr(cols1, C.c_int), ptr(vals, C.c_float),
                                       ptr(b, C.c_float)), "lsmr_create")
         self.h, self.m, self.n, self.nnz = h, m, n, len(vals)
+
+    @classmethod
+    def from_plan(cls, plan, obst=None, threshold0=None, weight=None):
+        """Device-resident host glue (main.f90:361-466): the plan's COO stays in HBM."""
+        pb = plan.pb
+        obst = _c(pb.obst if obst is None else obst, F32)
+        h = C.c_void_p()
+        check(lib().dsurf_lsmr_create_from_plan(
+            C.byref(h), plan.h, ptr(obst, C.c_float),
+            C.c_float(pb.threshold if threshold0 is None else threshold0),
+            C.c_float(pb.weight if weight is None else weight)), "lsmr_create_from_plan")
+        self = cls.__new__(cls)
+        g = plan.glue_results(want_vectors=False)
+        self.h, self.m, self.n, self.nnz = h, g["m"], pb.maxvp, g["nar"]
+        return self
 
     def close(self):
         if self.h:

@@ -45,7 +45,7 @@ __global__ void k_velv(const double *__restrict__ pv, float *__restrict__ velv, 
 }
 
 __global__ void k_dice(const float *__restrict__ velv, float *__restrict__ veln, int nvx, int nvz,
-                       int nnx, int nnz) {
+                       int nnx, int nnz, int kGd) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= nnx * nnz) return;
   const int stz = gid % nnz + 1, stx = gid / nnz + 1;
@@ -74,7 +74,7 @@ int launch_dice(cudaStream_t st, const Geom &g, const double *d_pv_map, float *d
   const int nv = g.nx * g.ny;
   k_velv<<<(nv + 255) / 256, 256, 0, st>>>(d_pv_map, d_velv, nv);
   const int nn = g.nnx * g.nnz;
-  k_dice<<<(nn + 255) / 256, 256, 0, st>>>(d_velv, d_veln, g.nvx, g.nvz, g.nnx, g.nnz);
+  k_dice<<<(nn + 255) / 256, 256, 0, st>>>(d_velv, d_veln, g.nvx, g.nvz, g.nnx, g.nnz, g.gd);
   return DSURF_OK;
 }
 
@@ -735,7 +735,7 @@ k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__
   const int nrnx = d.nrnx, nrnz = d.nrnz;
   // ---- bsplrefine (:1562-1628): refined velocities + reset refined node states
   {
-    const int nrr = kGd * kSgdl;  // 64
+    const int nrr = g.gd * kSgdl;  // 64 (40 for synthetic)
     const int origx = (d.vnl - 1) * kSgdl + 1, origz = (d.vnt - 1) * kSgdl + 1;
     const int ldv = g.nvx + 2;
     for (int n = lane; n < nrnx * nrnz; n += 32) {
@@ -1235,7 +1235,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
   const int nrnx = d.nrnx, nrnz = d.nrnz;
   // ---- bsplrefine (:1562-1628)
   {
-    const int nrr = kGd * kSgdl;
+    const int nrr = g.gd * kSgdl;
     const int origx = (d.vnl - 1) * kSgdl + 1, origz = (d.vnt - 1) * kSgdl + 1;
     const int ldv = g.nvx + 2;
     for (int n = gl; n < nrnx * nrnz; n += kG) {

@@ -787,6 +787,7 @@ struct dsurf_lsmr_sys {
   int rank = 0, nranks = 1;
   DevBuf<float> vpart;
   DevBuf<double> red;
+  bool solved = false;
   ~dsurf_lsmr_sys() {
     if (own_stream && st) cudaStreamDestroy(st);
   }
@@ -959,6 +960,10 @@ int lsmr_sys_create_dev(dsurf_lsmr_sys **out, int m, int n, long long nnz, const
 }
 }  // namespace dsurf
 
+namespace dsurf {
+float *lsmr_x_dev(dsurf_lsmr_sys *s) { return (s && s->solved) ? s->xout.p : nullptr; }
+}  // namespace dsurf
+
 extern "C" int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar, const int *rows1,
                                  const int *cols1, const float *vals, const float *b) {
   DS_CHECK(ensure_device());
@@ -1122,14 +1127,13 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   cudaEventRecord(e1, st);
   LsmrScalars hs;
   DS_CUDA(cudaMemcpyAsync(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost, st));
-  if (x_host) {
-    const float *xsrc = s->x.p;
-    if (s->K > 0) {  // back to the reference's column order k*P + pos
-      k_unpermute<<<(s->n + 255) / 256, 256, 0, st>>>(s->x.p, s->xout.p, s->P, s->K);
-      xsrc = s->xout.p;
-    }
-    DS_CUDA(cudaMemcpyAsync(x_host, xsrc, (size_t)s->n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
+  // x in the reference's column order k*P + pos stays in xout (read by the device-side model update)
+  if (s->K > 0)
+    k_unpermute<<<(s->n + 255) / 256, 256, 0, st>>>(s->x.p, s->xout.p, s->P, s->K);
+  else
+    DS_CUDA(cudaMemcpyAsync(s->xout.p, s->x.p, (size_t)s->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  s->solved = true;
+  if (x_host) DS_CUDA(cudaMemcpyAsync(x_host, s->xout.p, (size_t)s->n * sizeof(float), cudaMemcpyDeviceToHost, st));
   DS_CUDA(cudaStreamSynchronize(st));
   DS_CUDA(cudaGetLastError());
   if (gexec) cudaGraphExecDestroy(gexec);

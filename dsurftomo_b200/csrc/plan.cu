@@ -15,10 +15,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <vector>
 #include "../../include/dsurftomo_b200.h"
 #include "common.cuh"
 #include "plan.cuh"
+#include "glue.cuh"
 
 namespace dsurf {
 int launch_coef(cudaStream_t st, const float *d_vels, int nx, int ny, int nz, int brocher, float *coe_a,
@@ -53,6 +55,7 @@ struct SweepRef {
 struct dsurf_plan {
   Geom g{};
   int nz = 0, kmaxT[4] = {0, 0, 0, 0}, kmax = 0, nsrc = 0, nrcf = 0;
+  bool forward_only = false;  // subroutine synthetic (CalSurfG.f90:2412-2865): times only, gdx = gdz = 5
   float minthk = 0;
   std::vector<float> depz;
   std::vector<double> tper[4];
@@ -98,11 +101,22 @@ struct dsurf_plan {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evt0 = nullptr, evt1 = nullptr;
   double ms_sweeps_total = 0;
+  // device-resident host glue (glue.cu)
+  DevBuf<float> g_obst, g_cbst, g_datw, g_sorted, g_sval;
+  DevBuf<double> g_norm;
+  DevBuf<int> g_srow, g_scol;
+  DevBuf<char> g_tmp;
+  long long g_nsm = 0;
+  int g_count3 = 0;
+  float g_weight = -1.0f;
+  bool g_valid = false;
+  GlueStats g_stats{};
 };
 
 static const float kPi = 3.1415926535898f;  // CalSurfG.f90:196
 
-static void make_geom(Geom &g, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd) {
+static void make_geom(Geom &g, int nx, int ny, float goxd, float gozd, float dvxd, float dvzd, int gd) {
+  g.gd = gd;
   g.nx = nx;
   g.ny = ny;
   g.nvx = nx - 2;
@@ -112,12 +126,12 @@ static void make_geom(Geom &g, int nx, int ny, float goxd, float gozd, float dvx
   g.dvz = dvzd * kPi / 180.0f;
   g.gox = (90.0f - goxd) * kPi / 180.0f;
   g.goz = gozd * kPi / 180.0f;
-  g.nnx = (g.nvx - 1) * kGd + 1;
-  g.nnz = (g.nvz - 1) * kGd + 1;
-  g.dnx = g.dvx / (float)kGd;
-  g.dnz = g.dvz / (float)kGd;
-  g.drnx = g.dvx / (float)(kGd * kSgdl);
-  g.drnz = g.dvz / (float)(kGd * kSgdl);
+  g.nnx = (g.nvx - 1) * gd + 1;
+  g.nnz = (g.nvz - 1) * gd + 1;
+  g.dnx = g.dvx / (float)gd;
+  g.dnz = g.dvz / (float)gd;
+  g.drnx = g.dvx / (float)(gd * kSgdl);
+  g.drnz = g.dvz / (float)(gd * kSgdl);
   float dpl = g.dnx * g.earth;                        // :1705-1709 / :1864-1869
   float rd1 = g.dnz * g.earth * sinf(g.gox);
   if (rd1 < dpl) dpl = rd1;
@@ -162,18 +176,19 @@ static int make_sweep(const Geom &g, float x, float z, SweepDesc &d, float *rist
   return DSURF_OK;
 }
 
-extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const float *vels, float goxdf,
-                                 float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
-                                 int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
-                                 const double *tLg, const int *wavetype, const int *igrt, const int *periods,
-                                 const float *depz, float minthk, const float *scxf, const float *sczf,
-                                 const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
-                                 int kmax, int nsrcsurf, int nrcf) {
+static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const float *vels, float goxdf,
+                            float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                            int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                            const double *tLg, const int *wavetype, const int *igrt, const int *periods,
+                            const float *depz, float minthk, const float *scxf, const float *sczf,
+                            const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                            int kmax, int nsrcsurf, int nrcf, int gd, bool forward_only) {
   DS_CHECK(ensure_device());
   if (!out || nx < 4 || ny < 4 || nz < 2 || kmax != kmaxRc + kmaxRg + kmaxLc + kmaxLg) return DSURF_ERR_BAD_ARG;
-  dsurf_lsmr_hint_geometry(nx, ny, nz);
+  if (!forward_only) dsurf_lsmr_hint_geometry(nx, ny, nz);
   auto *p = new dsurf_plan();
-  make_geom(p->g, nx, ny, goxdf, gozdf, dvxdf, dvzdf);
+  p->forward_only = forward_only;
+  make_geom(p->g, nx, ny, goxdf, gozdf, dvxdf, dvzdf, gd);
   p->nz = nz;
   p->kmaxT[0] = kmaxRc;
   p->kmaxT[1] = kmaxRg;
@@ -188,9 +203,10 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
   for (int t = 0; t < 4; t++)
     if (p->kmaxT[t] > 0) p->tper[t].assign(tp[t], tp[t] + p->kmaxT[t]);  // never touch t when kmaxX == 0
   // pv arrays: Rc and Lc are dimensioned with kmax columns in the reference (:1003-1004)
-  p->pvcols[0] = kmax;
+  // (subroutine synthetic dimensions every pv array by its own kmaxX, :2481)
+  p->pvcols[0] = forward_only ? std::max(kmaxRc, 1) : kmax;
   p->pvcols[1] = std::max(kmaxRg, 1);
-  p->pvcols[2] = kmax;
+  p->pvcols[2] = forward_only ? std::max(kmaxLc, 1) : kmax;
   p->pvcols[3] = std::max(kmaxLg, 1);
   for (int t = 0; t < 4; t++) p->mapslot[t].assign(p->pvcols[t], -1);
   // ---- flatten the gather loop nest and assign velocity-map slots
@@ -227,7 +243,7 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
         return DSURF_ERR_BAD_ARG;
       }
       slot_of(type, gi.per - 1);
-      if (gr == 1) slot_of(type == 1 ? 0 : 2, gi.per - 1);  // ig = 2 propagates on the phase map (:1177-1185)
+      if (gr == 1 && !forward_only) slot_of(type == 1 ? 0 : 2, gi.per - 1);  // ig = 2: phase map (:1177-1185)
       for (int r = 0; r < gi.nrc; r++) {
         const size_t i3 = i2 * nrcf + r;
         p->rcx.push_back(rcxf[i3]);
@@ -249,8 +265,10 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
     bad |= p->pv[t].reserve(ncol * p->pvcols[t]) != cudaSuccess;
     if (kt > 0) {
       bad |= p->dt[t].reserve(kt) != cudaSuccess;
-      for (int q = 0; q < 3; q++) bad |= p->sen[t][q].reserve(ncol * kt * nz) != cudaSuccess;
-      bad |= p->S[t].reserve(ncol * kt * (nz - 1)) != cudaSuccess;
+      if (!forward_only) {
+        for (int q = 0; q < 3; q++) bad |= p->sen[t][q].reserve(ncol * kt * nz) != cudaSuccess;
+        bad |= p->S[t].reserve(ncol * kt * (nz - 1)) != cudaSuccess;
+      }
     }
   }
   bad |= p->velv_all.reserve(std::max<size_t>(1, p->nmaps) * ncol) != cudaSuccess;
@@ -303,7 +321,7 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
   cudaMemGetInfo(&freeb, &totalb);
   p->hcap = 8 * (p->g.nnx + p->g.nnz) + 1024;
   if (const char *hc = getenv("DSURF_HCAP")) p->hcap = std::max(16, atoi(hc));  // test hook: force heap-slab growth
-  const size_t fdm_per_ray = (size_t)(p->g.nvz + 2) * (p->g.nvx + 2) * sizeof(float);
+  const size_t fdm_per_ray = forward_only ? sizeof(float) : (size_t)(p->g.nvz + 2) * (p->g.nvx + 2) * sizeof(float);
   int maxnrc = 1;
   for (auto &gi : p->gathers) maxnrc = std::max(maxnrc, gi.nrc);
   const size_t per_slot = Nc * sizeof(int2) + (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) +
@@ -311,7 +329,7 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
                           (size_t)maxnrc * (fdm_per_ray + sizeof(RayDesc) + 64);
   const size_t budget = std::min<size_t>((size_t)(freeb * 0.6), (size_t)100 << 30);
   long long nsw_total = 0;
-  for (auto &gi : p->gathers) nsw_total += gi.igr == 1 ? 2 : 1;
+  for (auto &gi : p->gathers) nsw_total += (gi.igr == 1 && !forward_only) ? 2 : 1;
   long long ms = (long long)(budget / per_slot);
   ms = std::min<long long>(ms, std::max<long long>(nsw_total, 1));
   {  // batches of at most one resident wave (larger launches would run as equal-length waves)
@@ -348,6 +366,32 @@ extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const
   }
   *out = p;
   return DSURF_OK;
+}
+
+extern "C" int dsurf_plan_create(dsurf_plan **out, int nx, int ny, int nz, const float *vels, float goxdf,
+                                 float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                                 int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                                 const double *tLg, const int *wavetype, const int *igrt, const int *periods,
+                                 const float *depz, float minthk, const float *scxf, const float *sczf,
+                                 const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                                 int kmax, int nsrcsurf, int nrcf) {
+  return plan_create_impl(out, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, kmaxRg, kmaxLc, kmaxLg, tRc, tRg,
+                          tLc, tLg, wavetype, igrt, periods, depz, minthk, scxf, sczf, rcxf, rczf, nrc1, nsrcsurf1,
+                          kmax, nsrcsurf, nrcf, kGd, false);
+}
+
+// forward-only plan of subroutine synthetic (CalSurfG.f90:2412-2865): gdx = gdz = 5, dispersion
+// maps by caldespersion (group maps for the group types), one sweep per gather, times only
+extern "C" int dsurf_plan_create_forward(dsurf_plan **out, int nx, int ny, int nz, const float *vels, float goxdf,
+                                         float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                                         int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                                         const double *tLg, const int *wavetype, const int *igrt,
+                                         const int *periods, const float *depz, float minthk, const float *scxf,
+                                         const float *sczf, const float *rcxf, const float *rczf, const int *nrc1,
+                                         const int *nsrcsurf1, int kmax, int nsrcsurf, int nrcf) {
+  return plan_create_impl(out, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, kmaxRg, kmaxLc, kmaxLg, tRc, tRg,
+                          tLc, tLg, wavetype, igrt, periods, depz, minthk, scxf, sczf, rcxf, rczf, nrc1, nsrcsurf1,
+                          kmax, nsrcsurf, nrcf, 5, true);
 }
 
 extern "C" int dsurf_plan_destroy(dsurf_plan *p) {
@@ -387,6 +431,24 @@ extern "C" int dsurf_plan_dispersion(dsurf_plan *p) {
   const Geom &g = p->g;
   cudaEventRecord(p->ev[0], p->st);
   const int iw[4] = {2, 2, 1, 1}, ig[4] = {0, 1, 0, 1};
+  if (p->forward_only) {  // subroutine synthetic: caldespersion per data type (:2552-2613)
+    for (int t = 0; t < 4; t++)
+      if (p->kmaxT[t] > 0)
+        DS_CHECK(run_dispersion(p->st, p->vels.p, g.nx, g.ny, p->nz, p->tables, iw[t], ig[t], p->kmaxT[t], p->dt[t].p,
+                                false, p->pv[t].p, nullptr, nullptr, nullptr, p->cgbuf));
+    cudaEventRecord(p->ev[1], p->st);
+    DS_CHECK(dice_maps(p));
+    cudaEventRecord(p->ev[2], p->st);
+    DS_CUDA(cudaStreamSynchronize(p->st));
+    DS_CUDA(cudaGetLastError());
+    float msf = 0;
+    cudaEventElapsedTime(&msf, p->ev[0], p->ev[1]);
+    p->ms[0] = msf;
+    cudaEventElapsedTime(&msf, p->ev[1], p->ev[2]);
+    p->ms[1] = msf;
+    p->disp_done = true;
+    return DSURF_OK;
+  }
   for (int t = 0; t < 4; t++) {
     const int kt = p->kmaxT[t];
     if (kt <= 0) continue;
@@ -429,13 +491,22 @@ extern "C" int dsurf_plan_set_dispersion(dsurf_plan *p, int type, const double *
   const size_t ns = ncol * p->kmaxT[type] * p->nz;
   const double *src[3] = {sen_vs, sen_vp, sen_rho};
   for (int q = 0; q < 3; q++)
-    if (src[q] && ns > 0) DS_CUDA(cudaMemcpy(p->sen[type][q].p, src[q], ns * sizeof(double), cudaMemcpyHostToDevice));
+    if (src[q] && ns > 0) {
+      if (p->forward_only) return DSURF_ERR_BAD_ARG;  // a forward-only plan holds no depth kernels
+      DS_CUDA(cudaMemcpy(p->sen[type][q].p, src[q], ns * sizeof(double), cudaMemcpyHostToDevice));
+    }
   p->maps_diced = false;
   return DSURF_OK;
 }
 extern "C" int dsurf_plan_finalize_dispersion(dsurf_plan *p) {
   if (!p) return DSURF_ERR_BAD_ARG;
   const Geom &g = p->g;
+  if (p->forward_only) {
+    DS_CHECK(dice_maps(p));
+    DS_CUDA(cudaStreamSynchronize(p->st));
+    p->disp_done = true;
+    return DSURF_OK;
+  }
   const int brocher = p->depz[p->nz - 2] < 35.0f ? 1 : 0;
   DS_CHECK(launch_coef(p->st, p->vels.p, g.nx, g.ny, p->nz, brocher, p->coe_a.p, p->coe_rho.p));
   for (int t = 0; t < 4; t++)
@@ -466,7 +537,7 @@ extern "C" int dsurf_plan_num_gathers(const dsurf_plan *p) { return p ? (int)p->
 extern "C" int dsurf_plan_num_sweeps(const dsurf_plan *p, int g0, int g1) {
   if (!p) return 0;
   int n = 0;
-  for (int g = std::max(g0, 0); g < std::min(g1, (int)p->gathers.size()); g++) n += p->gathers[g].igr == 1 ? 2 : 1;
+  for (int g = std::max(g0, 0); g < std::min(g1, (int)p->gathers.size()); g++) n += (p->gathers[g].igr == 1 && !p->forward_only) ? 2 : 1;
   return n;
 }
 extern "C" int64_t dsurf_plan_nar(const dsurf_plan *p) { return p ? p->nar : 0; }
@@ -560,7 +631,7 @@ static int append_gather(dsurf_plan *p, int gidx, int only_ig, std::vector<Sweep
                          std::vector<RayDesc> &hrays, std::vector<float> &hristr, std::vector<int> &hrayS,
                          std::vector<int> &hrayrow) {
   const GatherInfo &gi = p->gathers[gidx];
-  const int igroup = gi.igr == 1 ? 2 : 1;
+  const int igroup = (gi.igr == 1 && !p->forward_only) ? 2 : 1;
   for (int ig = 1; ig <= igroup; ig++) {
     if (only_ig && ig != only_ig) continue;
     SweepDesc d;
@@ -576,6 +647,7 @@ static int append_gather(dsurf_plan *p, int gidx, int only_ig, std::vector<Sweep
     d.nrc = gi.nrc;
     d.do_times = (ig == 1) ? 1 : 0;
     d.do_rays = (gi.igr == 0 || ig == 2) ? 1 : 0;
+    if (p->forward_only) d.do_rays = 0;
     const int slot = (int)hsw.size();
     hsw.push_back(d);
     for (int r = 0; r < gi.nrc; r++) {
@@ -615,14 +687,14 @@ extern "C" int dsurf_plan_sweeps(dsurf_plan *p, int g0, int g1) {
     hrayrow.clear();
     while (g < g1) {
       const GatherInfo &gi = p->gathers[g];
-      const int ns = gi.igr == 1 ? 2 : 1;
+      const int ns = (gi.igr == 1 && !p->forward_only) ? 2 : 1;
       if (!hsw.empty() && ((int)hsw.size() + ns > p->maxslots || (int)hrays.size() + ns * gi.nrc > p->maxrays)) break;
       DS_CHECK(append_gather(p, g, 0, hsw, hrays, hristr, hrayS, hrayrow));
       g++;
     }
     // group gathers trace rays only in pass 2 and times only in pass 1: drop the unused RayDescs
     // per sweep inside the kernels via do_times/do_rays (both kept so that rows stay aligned).
-    DS_CHECK(run_batch(p, hsw, hrays, hristr, hrayS, hrayrow, true, &launches));
+    DS_CHECK(run_batch(p, hsw, hrays, hristr, hrayS, hrayrow, !p->forward_only, &launches));
     nsolved += (int)hsw.size();
   }
   cudaEventRecord(p->evt1, p->st);
@@ -772,8 +844,210 @@ extern "C" void calsurfg_(const int *nx, const int *ny, const int *nz, const int
   }
 }
 
-// not yet implemented in round 1: device-resident host glue
-extern "C" int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **, dsurf_plan *, const float *, float, float) {
-  set_error(__FILE__, __LINE__, "dsurf_lsmr_create_from_plan: not implemented yet");
-  return DSURF_ERR_BAD_ARG;
+// ------------------------------------------------------------------------------- synthetic drop-in
+// subroutine synthetic (CalSurfG.f90:2412-2865): forward times through `vels` on the gd = 5
+// propagation grid, obst(i) = t + t*gaussian()*noiselevel, and the velmap2d{Rc,Rg,Lc,Lg}.dat maps.
+namespace {
+// gaussian.f90: Box-Muller on two uniform deviates, second deviate discarded (use_last is reset on
+// every call).  The reference draws from gfortran's random_number, whose stream is not reproducible
+// outside libgfortran; this is a splitmix64-seeded xoshiro256** -- same distribution, other draws.
+struct Rng {
+  uint64_t s[4];
+  explicit Rng(uint64_t seed) {
+    for (auto &v : s) {
+      seed += 0x9e3779b97f4a7c15ull;
+      uint64_t z = seed;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      v = z ^ (z >> 31);
+    }
+  }
+  static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  float uniform() {  // [0, 1)
+    const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl(s[3], 45);
+    return (float)(r >> 40) * (1.0f / 16777216.0f);
+  }
+  float gaussian() {
+    float x1 = 0, w = 2.0f;
+    while (w >= 1.0f) {
+      const float n1 = uniform(), n2 = uniform();
+      x1 = 2.0f * n1 - 1.0f;
+      const float x2 = 2.0f * n2 - 1.0f;
+      w = x1 * x1 + x2 * x2;
+    }
+    w = powf((-2.0f * logf(w)) / w, 0.5f);
+    return x1 * w;
+  }
+};
+}  // namespace
+
+extern "C" int dsurf_synthetic(int nx, int ny, int nz, int nparpi, const float *vels, float *obst, float goxdf,
+                               float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc, int kmaxLg,
+                               const double *tRc, const double *tRg, const double *tLc, const double *tLg,
+                               const int *wavetype, const int *igrt, const int *periods, const float *depz,
+                               float minthk, const float *scxf, const float *sczf, const float *rcxf,
+                               const float *rczf, const int *nrc1, const int *nsrcsurf1, int kmax, int nsrcsurf,
+                               int nrcf, float noiselevel, const char *outdir, uint64_t seed, int *rbint) {
+  (void)nparpi;
+  if (!obst) return DSURF_ERR_BAD_ARG;
+  dsurf_plan *p = nullptr;
+  DS_CHECK(dsurf_plan_create_forward(&p, nx, ny, nz, vels, goxdf, gozdf, dvxdf, dvzdf, kmaxRc, kmaxRg, kmaxLc, kmaxLg,
+                                     tRc, tRg, tLc, tLg, wavetype, igrt, periods, depz, minthk, scxf, sczf, rcxf, rczf,
+                                     nrc1, nsrcsurf1, kmax, nsrcsurf, nrcf));
+  int rc = dsurf_plan_dispersion(p);
+  if (rc == DSURF_OK && outdir) {  // velmap2dXX.dat, format (5f8.4) (:2557-2613)
+    static const char *names[4] = {"velmap2dRc.dat", "velmap2dRg.dat", "velmap2dLc.dat", "velmap2dLg.dat"};
+    const size_t ncol = (size_t)nx * ny;
+    for (int t = 0; t < 4 && rc == DSURF_OK; t++) {
+      const int kt = p->kmaxT[t];
+      if (kt <= 0) continue;
+      std::vector<double> pv(ncol * kt);
+      if (cudaMemcpy(pv.data(), p->pv[t].p, pv.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        rc = DSURF_ERR_CUDA;
+        break;
+      }
+      std::string path = std::string(outdir);
+      if (!path.empty() && path.back() != '/') path += "/";
+      path += names[t];
+      FILE *f = fopen(path.c_str(), "w");
+      if (!f) {
+        set_error(__FILE__, __LINE__, "cannot open velmap2d output file");
+        rc = DSURF_ERR_BAD_ARG;
+        break;
+      }
+      for (int k = 1; k <= kt; k++)
+        for (int j = 1; j <= ny - 2; j++)
+          for (int i = 1; i <= nx - 2; i++)
+            fprintf(f, "%8.4f%8.4f%8.4f%8.4f\n", gozdf + (float)(j - 1) * dvzdf, goxdf - (float)(i - 1) * dvxdf,
+                    p->tper[t][k - 1], pv[(size_t)(k - 1) * ncol + (size_t)(j + 1) * nx + i]);
+      fclose(f);
+    }
+  }
+  if (rc == DSURF_OK) rc = dsurf_plan_reset_rows(p);
+  if (rc == DSURF_OK) rc = dsurf_plan_sweeps(p, 0, dsurf_plan_num_gathers(p));
+  if (rc == DSURF_OK) rc = dsurf_plan_download(p, nullptr, nullptr, nullptr, obst, rbint);
+  if (rc == DSURF_OK && noiselevel != 0.0f) {
+    Rng rng(seed);
+    for (int i = 0; i < p->dall; i++) obst[i] = obst[i] + obst[i] * rng.gaussian() * noiselevel;
+  }
+  dsurf_plan_destroy(p);
+  return rc;
+}
+
+extern "C" void dsurf_fatal_(const int *rc);
+extern "C" void synthetic_(const int *nx, const int *ny, const int *nz, const int *nparpi, const float *vels,
+                           float *obst, const float *goxdf, const float *gozdf, const float *dvxdf,
+                           const float *dvzdf, const int *kmaxRc, const int *kmaxRg, const int *kmaxLc,
+                           const int *kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                           const double *tLg, const int *wavetype, const int *igrt, const int *periods,
+                           const float *depz, const float *minthk, const float *scxf, const float *sczf,
+                           const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                           const int *kmax, const int *nsrcsurf, const int *nrcf, const float *noiselevel) {
+  int rbint = 0;
+  int rc = dsurf_synthetic(*nx, *ny, *nz, *nparpi, vels, obst, *goxdf, *gozdf, *dvxdf, *dvzdf, *kmaxRc, *kmaxRg,
+                           *kmaxLc, *kmaxLg, tRc, tRg, tLc, tLg, wavetype, igrt, periods, depz, *minthk, scxf, sczf,
+                           rcxf, rczf, nrc1, nsrcsurf1, *kmax, *nsrcsurf, *nrcf, *noiselevel, ".", 20150131ull,
+                           &rbint);
+  if (rc != DSURF_OK) dsurf_fatal_(&rc);
+  if (rbint) {  // :2843-2850 (printed per gather in the reference)
+    printf(" Note that at least one two-point ray path\n tracked along the boundary of the model.\n"
+           " This class of path is unlikely to be\n a true path, and it is STRONGLY RECOMMENDED\n"
+           " that you adjust the dimensions of your grid\n to prevent this from occurring.\n");
+  }
+}
+
+// ------------------------------------------------------------------- device-resident host glue
+// main.f90:361-466 on the device: residual, percentile outlier weights, row scaling, DWS statistics,
+// smoothing rows appended behind the data rows, then the LSMR system is built straight from the
+// plan's COO in HBM.
+extern "C" int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **sys, dsurf_plan *p, const float *obst, float threshold0,
+                                           float weight) {
+  if (!sys || !p || !obst) return DSURF_ERR_BAD_ARG;
+  DS_CHECK(ensure_device());
+  const int dall = p->dall;
+  const int maxvp = p->g.nvx * p->g.nvz * (p->nz - 1);
+  if (dall < 2) return DSURF_ERR_BAD_ARG;
+  cudaStream_t st = p->st;
+  if (!p->g_srow.p || p->g_weight != weight) {  // smoothing rows: static per geometry and weight
+    std::vector<int> r, c;
+    std::vector<float> v;
+    glue_smoothing_rows(p->g.nx, p->g.ny, p->nz, dall, weight, r, c, v, &p->g_count3);
+    p->g_nsm = (long long)r.size();
+    if (p->g_srow.reserve(r.size()) || p->g_scol.reserve(r.size()) || p->g_sval.reserve(r.size())) {
+      set_error(__FILE__, __LINE__, "cudaMalloc failed (smoothing rows)");
+      return DSURF_ERR_CUDA;
+    }
+    DS_CUDA(cudaMemcpy(p->g_srow.p, r.data(), r.size() * sizeof(int), cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(p->g_scol.p, c.data(), c.size() * sizeof(int), cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(p->g_sval.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    p->g_weight = weight;
+  }
+  const int m = dall + p->g_count3;
+  if (p->g_obst.reserve(dall) || p->g_cbst.reserve(m) || p->g_datw.reserve(dall) || p->g_norm.reserve((size_t)maxvp + 2)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (glue vectors)");
+    return DSURF_ERR_CUDA;
+  }
+  DS_CUDA(cudaMemcpyAsync(p->g_obst.p, obst, (size_t)dall * sizeof(float), cudaMemcpyHostToDevice, st));
+  DS_CUDA(cudaMemsetAsync(p->g_cbst.p, 0, (size_t)m * sizeof(float), st));
+  DS_CHECK(glue_apply(st, dall, maxvp, p->nar, p->g_obst.p, p->dsurf.p, threshold0, p->rowidx.p, p->col.p, p->rw.p,
+                      p->g_cbst.p, p->g_datw.p, p->g_norm.p, p->g_sorted, p->g_tmp, &p->g_stats));
+  // append the smoothing rows behind the data rows (in place: the tail is scratch of the plan)
+  const long long nnz = p->nar + p->g_nsm;
+  if (nnz >= (1ll << 31)) {
+    set_error(__FILE__, __LINE__, "nar exceeds the int32 triplet count of the reference boundary");
+    return DSURF_ERR_CAPACITY;
+  }
+  if (p->rw.reserve((size_t)nnz, true, st) || p->col.reserve((size_t)nnz, true, st) ||
+      p->rowidx.reserve((size_t)nnz, true, st)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (COO growth for smoothing rows)");
+    return DSURF_ERR_CUDA;
+  }
+  DS_CUDA(cudaMemcpyAsync(p->rowidx.p + p->nar, p->g_srow.p, (size_t)p->g_nsm * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  DS_CUDA(cudaMemcpyAsync(p->col.p + p->nar, p->g_scol.p, (size_t)p->g_nsm * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  DS_CUDA(cudaMemcpyAsync(p->rw.p + p->nar, p->g_sval.p, (size_t)p->g_nsm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  p->g_valid = true;
+  return lsmr_sys_create_dev(sys, m, maxvp, nnz, p->rowidx.p, p->col.p, p->rw.p, p->g_cbst.p);
+}
+
+extern "C" int dsurf_plan_glue_results(dsurf_plan *p, float *cbst, float *datweight, float *stats4, int *m_out,
+                                       int64_t *nar_out) {
+  if (!p || !p->g_valid) return DSURF_ERR_BAD_ARG;
+  if (cbst) DS_CUDA(cudaMemcpy(cbst, p->g_cbst.p, (size_t)p->dall * sizeof(float), cudaMemcpyDeviceToHost));
+  if (datweight) DS_CUDA(cudaMemcpy(datweight, p->g_datw.p, (size_t)p->dall * sizeof(float), cudaMemcpyDeviceToHost));
+  if (stats4) {
+    stats4[0] = p->g_stats.q25;
+    stats4[1] = p->g_stats.q75;
+    stats4[2] = p->g_stats.maxnorm;
+    stats4[3] = p->g_stats.averdws;
+  }
+  if (m_out) *m_out = p->dall + p->g_count3;
+  if (nar_out) *nar_out = p->nar + p->g_nsm;
+  return DSURF_OK;
+}
+
+// main.f90:518-532 on the device: dv = solution of the last solve of `sys` (clipped to +-0.5 in
+// place), model clamped to [minvel, maxvel]; the plan's dispersion/maps are invalidated.
+extern "C" int dsurf_plan_update_model(dsurf_plan *p, dsurf_lsmr_sys *sys, float minvel, float maxvel, float *dv_host,
+                                       float *vels_host) {
+  if (!p || !sys) return DSURF_ERR_BAD_ARG;
+  float *d_dv = lsmr_x_dev(sys);
+  if (!d_dv) return DSURF_ERR_BAD_ARG;
+  const int maxvp = p->g.nvx * p->g.nvz * (p->nz - 1);
+  DS_CUDA(cudaStreamSynchronize(p->st));
+  DS_CHECK(glue_model_update(p->st, p->vels.p, d_dv, p->g.nx, p->g.ny, p->nz, minvel, maxvel));
+  if (dv_host) DS_CUDA(cudaMemcpyAsync(dv_host, d_dv, (size_t)maxvp * sizeof(float), cudaMemcpyDeviceToHost, p->st));
+  if (vels_host)
+    DS_CUDA(cudaMemcpyAsync(vels_host, p->vels.p, (size_t)p->g.nx * p->g.ny * p->nz * sizeof(float),
+                            cudaMemcpyDeviceToHost, p->st));
+  DS_CUDA(cudaStreamSynchronize(p->st));
+  p->disp_done = false;
+  p->maps_diced = false;
+  return DSURF_OK;
 }

@@ -29,13 +29,14 @@ int run_dispersion(cudaStream_t st, const float *d_vel, int nx, int ny, int nz, 
                    double *d_sen_vs, double *d_sen_vp, double *d_sen_rho, DevBuf<double> &cgbuf);
 
 // ---- propagation-grid geometry (globalp, CalSurfG.f90:1032-1063), all REAL*4, host-computed
-constexpr int kGd = 8;     // gdx = gdz (CalSurfG.f90:1032-1033)
+constexpr int kGd = 8;     // gdx = gdz of CalSurfG (CalSurfG.f90:1032-1033); subroutine synthetic uses 5 (:2497-2498)
 constexpr int kSgdl = 8;   // source grid dicing level (:1035)
 constexpr int kSgs = 8;    // extent of refined source grid (:1036)
 constexpr int kRefMax = 2 * kSgs * kSgdl + 1;  // 129
 
 struct Geom {
   int nx, ny, nvx, nvz, nnx, nnz;
+  int gd;                    // grid dicing gdx = gdz: 8 for CalSurfG, 5 for synthetic
   float gox, goz, dnx, dnz, dvx, dvz, earth;
   float drnx, drnz;          // refined spacing dvx/REAL(gdx*sgdl)
   float dpl_sr;              // srtimes' dpl (:1705-1709)

@@ -84,6 +84,17 @@ void __lsmrmodule_MOD_lsmr(const int *m, const int *n, const int *leniw, const i
 void aprod_(const int *mode, const int *m, const int *n, float *x, float *y, const int *leniw,
             const int *lenrw, const int *iw, const float *rw);
 
+/* replaces subroutine synthetic, src/CalSurfG.f90:2412-2415 (checkerboard forward run, ifsyn = 1,
+ * main.f90:338-342); writes velmap2d{Rc,Rg,Lc,Lg}.dat into the working directory like the reference */
+void synthetic_(const int *nx, const int *ny, const int *nz, const int *nparpi, const float *vels,
+                float *obst, const float *goxdf, const float *gozdf, const float *dvxdf,
+                const float *dvzdf, const int *kmaxRc, const int *kmaxRg, const int *kmaxLc,
+                const int *kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                const double *tLg, const int *wavetype, const int *igrt, const int *periods,
+                const float *depz, const float *minthk, const float *scxf, const float *sczf,
+                const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                const int *kmax, const int *nsrcsurf, const int *nrcf, const float *noiselevel);
+
 /* ------------------------------------------------------------------ (2) neutral C entry points */
 
 /* CalSurfG with an explicit COO capacity (maxnar = spfra*dall*nx*ny*nz in main.f90:287) and a
@@ -97,6 +108,22 @@ int dsurf_calsurfg(int nx, int ny, int nz, int nparpi, const float *vels, int *i
                    const float *scxf, const float *sczf, const float *rcxf, const float *rczf,
                    const int *nrc1, const int *nsrcsurf1, int kmax, int nsrcsurf, int nrcf,
                    int64_t maxnar, int *nar, int *rbint);
+
+/* subroutine synthetic with a status instead of STOP.  Forward-only: caldespersion maps of every
+ * data type (group maps for the group types), ONE eikonal solve per gather on the gdx = gdz = 5
+ * propagation grid (CalSurfG.f90:2497-2498), receiver times only.  obst(i) = t + t*gaussian()*noiselevel
+ * (gaussian.f90; the normal deviates come from a xoshiro256** stream seeded with `seed`, because
+ * gfortran's random_number stream cannot be reproduced outside libgfortran -- noiselevel = 0 is
+ * deterministic and parity-tested).  outdir: where velmap2dXX.dat are written (format 5f8.4,
+ * :2557-2613), NULL = do not write. */
+int dsurf_synthetic(int nx, int ny, int nz, int nparpi, const float *vels, float *obst, float goxdf,
+                    float gozdf, float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc,
+                    int kmaxLg, const double *tRc, const double *tRg, const double *tLc,
+                    const double *tLg, const int *wavetype, const int *igrt, const int *periods,
+                    const float *depz, float minthk, const float *scxf, const float *sczf,
+                    const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
+                    int kmax, int nsrcsurf, int nrcf, float noiselevel, const char *outdir,
+                    uint64_t seed, int *rbint);
 
 /* depthkernel / caldespersion (igr: 0 phase, 1 group; iwave: 1 Love, 2 Rayleigh).
  * sen_* may all be NULL (dispersion map only == caldespersion). */
@@ -135,6 +162,15 @@ int dsurf_plan_create(dsurf_plan **plan, int nx, int ny, int nz, const float *ve
                       const float *depz, float minthk, const float *scxf, const float *sczf,
                       const float *rcxf, const float *rczf, const int *nrc1, const int *nsrcsurf1,
                       int kmax, int nsrcsurf, int nrcf);
+/* forward-only plan (what dsurf_synthetic runs): gd = 5, maps only, one sweep per gather, times only */
+int dsurf_plan_create_forward(dsurf_plan **plan, int nx, int ny, int nz, const float *vels,
+                              float goxdf, float gozdf, float dvxdf, float dvzdf, int kmaxRc,
+                              int kmaxRg, int kmaxLc, int kmaxLg, const double *tRc,
+                              const double *tRg, const double *tLc, const double *tLg,
+                              const int *wavetype, const int *igrt, const int *periods,
+                              const float *depz, float minthk, const float *scxf, const float *sczf,
+                              const float *rcxf, const float *rczf, const int *nrc1,
+                              const int *nsrcsurf1, int kmax, int nsrcsurf, int nrcf);
 int dsurf_plan_destroy(dsurf_plan *plan);
 /* replace the model (vels[nz][ny][nx]) for the next outer iteration */
 int dsurf_plan_set_model(dsurf_plan *plan, const float *vels);
@@ -176,9 +212,23 @@ double dsurf_plan_last_sweeps_ms(const dsurf_plan *plan);
 typedef struct dsurf_lsmr_sys dsurf_lsmr_sys;
 int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar, const int *rows1,
                       const int *cols1, const float *vals, const float *b);
-/* same, taking the COO a plan holds in HBM plus device-side host glue (main.f90:361-466) */
+/* same, taking the COO a plan holds in HBM: the host glue of main.f90:361-466 (residual
+ * cbst = obst - dsyn, getpercentile outlier weights, rw *= datweight(row), DWS statistics,
+ * smoothing rows appended, right-hand side) runs on the device, so the matrix never leaves HBM
+ * between CalSurfG and LSMR.  obst: dall observed times (host).  The plan's rw is scaled in
+ * place, as the reference's main program does. */
 int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **sys, dsurf_plan *plan, const float *obst,
                                 float threshold0, float weight);
+/* results of the last dsurf_lsmr_create_from_plan (any pointer may be NULL): cbst(1:dall) after
+ * outlier rejection, datweight(1:dall), stats4 = {q25, q75, maxnorm, averdws} (main.f90:364,386-394),
+ * m = dall + count3, nar including the smoothing rows */
+int dsurf_plan_glue_results(dsurf_plan *plan, float *cbst, float *datweight, float *stats4, int *m,
+                            int64_t *nar);
+/* main.f90:518-532 on the device: dv = solution of the last dsurf_lsmr_solve of `sys`, clipped to
+ * +-0.5, added to the interior nodes of the plan's model, model clamped to [minvel, maxvel].
+ * dv_host (maxvp, clipped) and vels_host (nx*ny*nz, updated model) may be NULL. */
+int dsurf_plan_update_model(dsurf_plan *plan, dsurf_lsmr_sys *sys, float minvel, float maxvel,
+                            float *dv_host, float *vels_host);
 /* column-order hint (P = (nx-2)(ny-2) vertices, K = nz-1 depths) enabling the depth-blocked
  * sparse layout when n == P*K; set automatically by every dsurf_plan_create / CalSurfG call */
 int dsurf_lsmr_hint_geometry(int nx, int ny, int nz);

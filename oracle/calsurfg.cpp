@@ -348,3 +348,80 @@ extern "C" int oracle_calsurfg_pre(int nx, int ny, int nz, const float *vels, in
                        kmaxLg, pvp, senp, wavetype, igrt, periods, depz, scxf, sczf, rcxf, rczf, nrc1, nsrcsurf1,
                        kmax, nsrcsurf, nrcf, nar, nthreads, mode, rbint_out, stage_seconds, g_lo, g_hi, 0.0);
 }
+
+// subroutine synthetic (CalSurfG.f90:2412-2865), noise-free part: caldespersion per data type
+// (group maps for the group types, :2552-2613), then for every gather one eikonal solve on the
+// gdx = gdz = 5 propagation grid and srtimes for every receiver (:2629-2839).  obst(i) = t; the
+// caller adds the reference's t*gaussian()*noiselevel term (random_number stream, not restated).
+// pv_out (may be NULL): the four maps back to back, each [kmaxX][nx*ny].
+extern "C" int oracle_synthetic(int nx, int ny, int nz, const float *vels, float *obst, float goxdf, float gozdf,
+                                float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc, int kmaxLg,
+                                const double *tRc, const double *tRg, const double *tLc, const double *tLg,
+                                const int *wavetype, const int *igrt, const int *periods, const float *depz,
+                                float minthk, const float *scxf, const float *sczf, const float *rcxf,
+                                const float *rczf, const int *nrc1, const int *nsrcsurf1, int kmax, int nsrcsurf,
+                                int nrcf, int nthreads, double *pv_out) {
+  const size_t ncol = (size_t)nx * ny;
+  const int kt[4] = {kmaxRc, kmaxRg, kmaxLc, kmaxLg};
+  const double *tp[4] = {tRc, tRg, tLc, tLg};
+  const int iwave[4] = {2, 2, 1, 1}, igr[4] = {0, 1, 0, 1};
+  std::vector<double> pv[4];
+  for (int t = 0; t < 4; t++) {
+    if (kt[t] <= 0) continue;
+    pv[t].assign(ncol * kt[t], 0.0);
+    oracle_caldespersion(nx, ny, nz, vels, pv[t].data(), iwave[t], igr[t], kt[t], tp[t], depz, minthk, nthreads);
+  }
+  if (pv_out) {
+    size_t o = 0;
+    for (int t = 0; t < 4; t++) {
+      for (size_t i = 0; i < pv[t].size(); i++) pv_out[o + i] = pv[t][i];
+      o += pv[t].size();
+    }
+  }
+  struct G { int knumi, srcnum, row; };
+  std::vector<G> gs;
+  int row = 0;
+  for (int knumi = 1; knumi <= kmax; knumi++)
+    for (int srcnum = 1; srcnum <= nsrcsurf1[knumi - 1]; srcnum++) {
+      gs.push_back({knumi, srcnum, row});
+      row += nrc1[(size_t)(knumi - 1) * nsrcsurf + (srcnum - 1)];
+    }
+  int err = 0;
+  if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+  {
+    Fmm f;
+    f.setup(nx, ny, goxdf, gozdf, dvxdf, dvzdf, 5);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+    for (long g = 0; g < (long)gs.size(); g++) {
+      const size_t i2 = (size_t)(gs[g].knumi - 1) * nsrcsurf + (gs[g].srcnum - 1);
+      const int wt = wavetype[i2], gr = igrt[i2], per = periods[i2];
+      int t = -1;
+      if (wt == 2 && gr == 0) t = 0;
+      if (wt == 2 && gr == 1) t = 1;
+      if (wt == 1 && gr == 0) t = 2;
+      if (wt == 1 && gr == 1) t = 3;
+      if (t < 0 || kt[t] <= 0) continue;
+      const float x = scxf[i2], z = sczf[i2];
+      f.solve_source(&pv[t][(size_t)(per - 1) * ncol], x, z);
+      if (!f.error)
+        for (int istep = 1; istep <= nrc1[i2]; istep++) {
+          const size_t i3 = i2 * nrcf + (istep - 1);
+          obst[gs[g].row + istep - 1] = f.srtimes(x, z, rcxf[i3], rczf[i3]);
+          if (f.error) break;
+        }
+      if (f.error) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        err = f.error;
+        f.error = 0;
+      }
+    }
+  }
+  return err;
+}

@@ -21,8 +21,8 @@ static inline void bspline4(float u, float o[5]) {  // CalSurfG.f90:1510-1513 (a
 }
 
 // CalSurfG.f90:1032-1094
-void Fmm::setup(int nx, int ny, float goxdf, float gozdf, float dvxdf, float dvzdf) {
-  gdx = 8; gdz = 8; asgr = 1; sgdl = 8; sgs = 8; earth = 6371.0f; fom = 1; snb = 0.5f;
+void Fmm::setup(int nx, int ny, float goxdf, float gozdf, float dvxdf, float dvzdf, int gd) {
+  gdx = gd; gdz = gd; asgr = 1; sgdl = 8; sgs = 8; earth = 6371.0f; fom = 1; snb = 0.5f;
   goxd = goxdf; gozd = gozdf; dvxd = dvxdf; dvzd = dvzdf;
   nvx = nx - 2;
   nvz = ny - 2;

@@ -36,7 +36,8 @@ struct Fmm {
   inline int &SR(int iz, int ix) { return nstsr[(size_t)(ix - 1) * ld + (iz - 1)]; }
   inline float &VV(int i, int j) { return velv[(size_t)j * (nvz + 2) + i]; }
 
-  void setup(int nx, int ny, float goxdf, float gozdf, float dvxdf, float dvzdf);  // :1032-1094
+  // :1032-1094; gd = gdx = gdz: 8 in CalSurfG (:1032-1033), 5 in subroutine synthetic (:2497-2498)
+  void setup(int nx, int ny, float goxdf, float gozdf, float dvxdf, float dvzdf, int gd = 8);
   void gridder(const double *pv);                                                   // :1460-1553
   void bsplrefine();                                                                // :1562-1628
   void travel(float scx, float scz, int urg);                                       // :288-487

@@ -71,6 +71,16 @@ int oracle_calsurfg(int nx, int ny, int nz, int nparpi, const float *vels, int *
                     const int *nrc1, const int *nsrcsurf1, int kmax, int nsrcsurf, int nrcf,
                     int *nar, int nthreads, int mode, int *rbint_out, double *stage_seconds);
 
+/* subroutine synthetic, CalSurfG.f90:2412-2865 (noise-free part): forward times on the gd = 5
+ * propagation grid through caldespersion maps; pv_out (may be NULL) receives the four maps. */
+int oracle_synthetic(int nx, int ny, int nz, const float *vels, float *obst, float goxdf, float gozdf,
+                     float dvxdf, float dvzdf, int kmaxRc, int kmaxRg, int kmaxLc, int kmaxLg,
+                     const double *tRc, const double *tRg, const double *tLc, const double *tLg,
+                     const int *wavetype, const int *igrt, const int *periods, const float *depz,
+                     float minthk, const float *scxf, const float *sczf, const float *rcxf,
+                     const float *rczf, const int *nrc1, const int *nsrcsurf1, int kmax, int nsrcsurf,
+                     int nrcf, int nthreads, double *pv_out);
+
 /* aprod.f90:7 */
 void oracle_aprod(int mode, int m, int n, float *x, float *y, int leniw, int lenrw, const int *iw,
                   const float *rw);

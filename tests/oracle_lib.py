@@ -166,6 +166,26 @@ def calsurfg(pb, vels=None, nthreads=1, mode=0, maxnar=None):
                 nrays=int(st[5]))
 
 
+def synthetic(pb, vels=None, nthreads=1):
+    """Oracle `synthetic` (noise-free): forward times through `vels` on the gd = 5 grid."""
+    vels = np.ascontiguousarray(pb.vsf if vels is None else vels, np.float32)
+    obst = np.zeros(pb.dall, np.float32)
+    dummy = np.zeros(1, np.float64)
+    tRc, tRg, tLc, tLg = (np.ascontiguousarray(t if len(t) else dummy, np.float64)
+                          for t in (pb.tRc, pb.tRg, pb.tLc, pb.tLg))
+    pv = np.zeros(max(1, pb.kmax) * pb.nx * pb.ny, np.float64)
+    err = lib().oracle_synthetic(
+        C.c_int(pb.nx), C.c_int(pb.ny), C.c_int(pb.nz), _p(vels, C.c_float), _p(obst, C.c_float),
+        C.c_float(pb.goxd), C.c_float(pb.gozd), C.c_float(pb.dvxd), C.c_float(pb.dvzd),
+        C.c_int(pb.kmaxRc), C.c_int(pb.kmaxRg), C.c_int(pb.kmaxLc), C.c_int(pb.kmaxLg),
+        _p(tRc, C.c_double), _p(tRg, C.c_double), _p(tLc, C.c_double), _p(tLg, C.c_double),
+        _p(pb.wavetype, C.c_int), _p(pb.igrt, C.c_int), _p(pb.periods, C.c_int),
+        _p(pb.depz, C.c_float), C.c_float(pb.minthk), _p(pb.scxf, C.c_float), _p(pb.sczf, C.c_float),
+        _p(pb.rcxf, C.c_float), _p(pb.rczf, C.c_float), _p(pb.nrc1, C.c_int), _p(pb.nsrc1, C.c_int),
+        C.c_int(pb.kmax), C.c_int(pb.nsrc), C.c_int(pb.nrc), C.c_int(nthreads), _p(pv, C.c_double))
+    return dict(err=err, obst=obst, pv=pv.reshape(max(1, pb.kmax), pb.nx * pb.ny))
+
+
 def calsurfg_pre(pb, pv4, sen12, g_lo=-1, g_hi=-1, vels=None, nthreads=1, mode=1, maxnar=None):
     """Gather loop of CalSurfG on caller-provided dispersion results (bench CPU arm).
     pv4: 4 arrays [cols, ncol] (Rc, Rg, Lc, Lg); sen12: 12 arrays [nz, kmax_t, ncol] in the order

@@ -247,6 +247,83 @@ def test_outer_iteration_model_update(taipei):
     assert np.abs(vs_new / vs_ref - 1).max() <= 1e-5
 
 
+def test_synthetic_matches_oracle(taipei, tmp_path):
+    """subroutine synthetic (forward times on the gd = 5 grid, ifsyn = 1).
+    (a) through the drop-in entry with the library's own dispersion maps: <=1e-5 relative (the maps
+    differ by 1 ulp in a few columns, see test_surfdisp96_batch_matches_oracle); (b) the forward-only
+    plan fed with the oracle's maps: bit-exact times; (c) velmap2dRc.dat format and content."""
+    pb = taipei
+    vtrue = (pb.vsf * (1.0 + 0.05 * np.sin(np.arange(pb.nx))[None, None, :])).astype(np.float32)
+    ref = O.synthetic(pb, vels=vtrue, nthreads=8)
+    assert ref["err"] == 0
+    got = api.synthetic(pb, vels=vtrue, outdir=str(tmp_path))
+    assert np.abs(got["obst"] / ref["obst"] - 1).max() <= 1e-5
+    plan = api.Plan(pb, vels=vtrue, forward=True)
+    plan.set_dispersion(0, ref["pv"][: pb.kmaxRc], None, None, None)
+    plan.finalize_dispersion()
+    plan.reset_rows()
+    plan.sweeps()
+    assert plan.num_sweeps() == plan.num_gathers
+    exact = plan.download()
+    assert exact["nar"] == 0 and np.array_equal(exact["dsurf"], ref["obst"])
+    lines = open(tmp_path / "velmap2dRc.dat").read().splitlines()
+    assert len(lines) == pb.kmaxRc * (pb.nx - 2) * (pb.ny - 2) and all(len(l) == 32 for l in lines[:50])
+    first = [float(lines[0][8 * i:8 * i + 8]) for i in range(4)]
+    assert abs(first[0] - pb.gozd) < 1e-4 and abs(first[1] - pb.goxd) < 1e-4 and abs(first[2] - pb.tRc[0]) < 1e-4
+    assert abs(first[3] - ref["pv"][0][2 * pb.nx + 1]) < 1e-4
+    # noise: reproducible for a seed, zero-mean relative perturbation of the requested size
+    n1 = api.synthetic(pb, vels=vtrue, noiselevel=0.02, seed=7)["obst"]
+    n2 = api.synthetic(pb, vels=vtrue, noiselevel=0.02, seed=7)["obst"]
+    rel = n1 / got["obst"] - 1
+    assert np.array_equal(n1, n2) and abs(rel.mean()) < 3e-3 and 0.015 < rel.std() < 0.025
+
+
+def test_device_glue_matches_host_glue(taipei):
+    """residual / percentile weights / row scaling / smoothing rows / model update
+    on the device (LsmrSystem.from_plan, Plan.update_model) against the host mirror of
+    main.f90:361-466,518-532 fed with the same CalSurfG output: identical system, identical solve."""
+    pb = taipei
+    plan = api.Plan(pb)
+    plan.dispersion()
+    plan.reset_rows()
+    plan.sweeps()
+    raw = plan.download()
+    raw = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in raw.items()}
+    s = hostglue.host_glue(pb, raw["dsurf"], raw["row"], raw["col"], raw["rw"])
+    sysd = api.LsmrSystem.from_plan(plan)
+    g = plan.glue_results()
+    assert g["m"] == s["m"] and g["nar"] == len(s["vals"])
+    assert np.array_equal(g["cbst"], s["cbst"][: pb.dall])
+    assert np.array_equal(g["datweight"], s["datweight"])
+    q25, q75 = hostglue.getpercentile((pb.obst - raw["dsurf"]).astype(np.float32))
+    assert g["q25"] == q25 and g["q75"] == q75
+    norm = np.zeros(pb.maxvp, np.float64)
+    np.add.at(norm, s["cols"][: raw["nar"]] - 1, np.abs(s["vals"][: raw["nar"]]).astype(np.float64))
+    assert abs(g["maxnorm"] / norm.max() - 1) < 1e-6 and abs(g["averdws"] / norm.mean() - 1) < 1e-6
+    scaled = plan.download()  # the plan's rw is scaled in place like the reference's
+    assert np.array_equal(scaled["rw"], s["vals"][: raw["nar"]])
+    dev = sysd.solve(pb.damp)
+    sysh = api.LsmrSystem(s["m"], s["n"], s["rows"], s["cols"], s["vals"], s["cbst"])
+    host = sysh.solve(pb.damp)
+    assert dev["itn"] == host["itn"] and dev["istop"] == host["istop"]
+    assert np.array_equal(dev["x"], host["x"])
+    vs_dev, dv_dev = plan.update_model(sysd)
+    vs_host, dv_host = hostglue.model_update(pb, pb.vsf, host["x"])
+    assert np.array_equal(dv_dev, dv_host) and np.array_equal(vs_dev, vs_host)
+    # second outer iteration runs from the device-resident model
+    plan.dispersion()
+    plan.reset_rows()
+    plan.sweeps()
+    second = plan.download()
+    plan2 = api.Plan(pb, vels=vs_host)
+    plan2.dispersion()
+    plan2.reset_rows()
+    plan2.sweeps()
+    ref2 = plan2.download()
+    assert second["nar"] == ref2["nar"] and np.array_equal(second["dsurf"], ref2["dsurf"])
+    assert np.array_equal(second["rw"], ref2["rw"])
+
+
 @pytest.mark.parametrize("var", ["DSURF_EIKONAL_V1", "DSURF_EIKONAL_V2"])
 def test_reference_eikonal_variants_also_bit_exact(var):
     """The simple (v1: one warp per sweep), overlapped (v2) and sub-warp (v3, default: 8 lanes per

@@ -151,6 +151,23 @@ def _random_system(rng, m, n, nnz):
     return rows, cols, vals
 
 
+def test_synthetic_forward_times(taipei):
+    """subroutine synthetic (CalSurfG.f90:2412-2865) on the oracle: times through the start model on
+    the gd = 5 grid agree with CalSurfG's predicted times on the gd = 8 grid to the O(h)
+    discretisation error, the dispersion maps are caldespersion's, and every time is ~ distance /
+    (a velocity inside the map's range)."""
+    pb = taipei
+    syn = O.synthetic(pb, nthreads=8)
+    assert syn["err"] == 0
+    full = O.calsurfg(pb, nthreads=8, mode=1)
+    assert np.abs(syn["obst"] / full["dsurf"] - 1).max() < 0.03
+    pv = O.caldespersion(pb.vsf, 2, 0, pb.tRc, pb.depz, pb.minthk, nthreads=8)
+    assert np.array_equal(np.asarray(pv).reshape(pb.kmaxRc, -1), syn["pv"][: pb.kmaxRc])
+    vapp = pb.dist / syn["obst"]
+    interior = syn["pv"][: pb.kmaxRc].reshape(pb.kmaxRc, pb.ny, pb.nx)[:, 1:-1, 1:-1]
+    assert vapp.min() > 0.97 * interior.min() and vapp.max() < 1.03 * interior.max()
+
+
 def test_aprod_vs_scipy():
     rng = np.random.default_rng(1)
     m, n, nnz = 200, 50, 1500
