@@ -136,7 +136,7 @@ def run_reference(args, pb, pv4, sen12, blocks):
 
     O.lib()
     cores = os.cpu_count() or 1
-    per_block = max(1, min(cores // 2, 32))
+    per_block = 64  # gathers of every data type per step: ~10 s of work on 16-128 host threads
     nsw_tot, t_tot = 0, 0.0
     for s in range(args.warmup + args.steps):
         nsw, t = cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, s, cores)
@@ -338,13 +338,29 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         if comm:
             comm.close()
 
+    # ---------------- K1: dispersion + depth kernels of the whole model (FP64-bound)
+    disp = None
+    if args.dispersion and world == 1:
+        plan.set_model(pb.vsf)
+        plan.dispersion()
+        torch.cuda.synchronize()
+        dms = plan.timings()["dispersion_ms"]
+        ncol = pb.nx * pb.ny
+        kts = (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)
+        # curve evaluations: every column x (1 + 6 nz) model variants x periods; group-velocity
+        # types evaluate two phase curves per period (surfdisp96.f:227-229)
+        curves = ncol * (1 + 6 * pb.nz) * sum(k * (2 if t in (1, 3) else 1) for t, k in enumerate(kts))
+        disp = dict(ms=dms, columns=ncol, column_types_per_s=ncol * sum(1 for k in kts if k) / (dms / 1e3),
+                    period_roots_per_s=curves / (dms / 1e3), bound="fp64 alu/sfu",
+                    note="depthkernel for all data types of the model (one CalSurfG dispersion stage), 1 launch set")
+
     # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores
     cpu = None
     if world == 1 and not args.no_cpu:
         import oracle_lib as O
 
         cores = os.cpu_count() or 1
-        per_block = max(1, min(cores // 2, 32))
+        per_block = 64  # ~10 s of CPU work on 16-128 host threads
         nsw, t = cpu_sweep_sample(pb, pv4, sen12, tblocks, per_block, 0, cores)
         cpu = dict(value=nsw / t, unit="sweeps/s", cores=cores, kind="port",
                    sample=f"{per_block} gathers of each of {len(tblocks)} data types ({nsw} sweeps, {t:.1f} s), "
@@ -375,7 +391,7 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
                                                  "with host buffers (pinned outputs)"),
                    gpu_launches=int(launches), clocks=clocks,
                    stage_ms_per_step={k: v / args.steps for k, v in stage.items()}, wall_s_timed=wall,
-                   lsmr=lsmr, impl="b200")
+                   lsmr=lsmr, dispersion=disp, impl="b200")
         print(json.dumps(out))
     plan.close()
     if dist is not None:
@@ -392,6 +408,7 @@ def main():
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--lsmr-iters", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dispersion", dest="dispersion", action="store_false")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference" and rank != 0:

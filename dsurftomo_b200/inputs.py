@@ -101,19 +101,37 @@ class Problem:
         return int(F32(self.spfra) * F32(self.dall) * F32(self.nx) * F32(self.ny) * F32(self.nz))
 
 
+_LIBM = None
+
+
+def _libm_f32(name, nargs):
+    """REAL*4 intrinsic of gfortran == the C library's float routine (sinf, cosf, atan2f), applied
+    element-wise; numpy's own float32 kernels differ from glibc by an ulp on some arguments."""
+    global _LIBM
+    import ctypes
+    import ctypes.util
+
+    if _LIBM is None:
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    fn = getattr(_LIBM, name)
+    fn.restype = ctypes.c_float
+    fn.argtypes = [ctypes.c_float] * nargs
+    uf = np.frompyfunc(lambda *a: fn(*[float(v) for v in a]), nargs, 1)
+    return lambda *a: np.asarray(uf(*a), dtype=np.float64).astype(F32)
+
+
 def delsph(flat1, flon1, flat2, flon2):
     """delsph.f90:1-28 in REAL*4 (inputs: colatitude, longitude in radians)."""
     flat1, flon1, flat2, flon2 = (np.asarray(v, dtype=F32) for v in (flat1, flon1, flat2, flon2))
+    sin, cos, atan2 = _libm_f32("sinf", 1), _libm_f32("cosf", 1), _libm_f32("atan2f", 2)
     R = F32(6371.0)
     dlat = flat2 - flat1
     dlon = flon2 - flon1
     lat1 = PI32 / F32(2) - flat1
     lat2 = PI32 / F32(2) - flat2
-    a = np.sin(dlat / F32(2)) * np.sin(dlat / F32(2)) + np.sin(dlon / F32(2)) * np.sin(
-        dlon / F32(2)
-    ) * np.cos(lat1) * np.cos(lat2)
-    a = a.astype(F32)
-    c = F32(2) * np.arctan2(np.sqrt(a), np.sqrt(F32(1) - a)).astype(F32)
+    s1, s2 = sin(dlat / F32(2)), sin(dlon / F32(2))
+    a = (s1 * s1 + s2 * s2 * cos(lat1) * cos(lat2)).astype(F32)
+    c = (F32(2) * atan2(np.sqrt(a), np.sqrt(F32(1) - a))).astype(F32)
     return (R * c).astype(F32)
 
 

@@ -1,0 +1,135 @@
+"""the Fortran-free main program (dsurftomo_b200/bin/dsurftomo_b200,
+source dsurftomo_b200/csrc/driver.cpp) -- readers, writers and the outer loop of src/main.f90.
+
+CPU tests: the C++ readers against the Python mirror of main.f90:134-321 (inputs.read_problem),
+the list-directed REAL*4 formatter against known gfortran output, loud failure without a GPU.
+GPU test: two Taipei outer iterations through the binary against the oracle chain
+(oracle CalSurfG -> host glue -> oracle LSMR -> model update)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import ROOT, has_gpu
+from dsurftomo_b200 import hostglue, inputs
+
+BIN = os.path.join(ROOT, "dsurftomo_b200", "bin", "dsurftomo_b200")
+TAIPEI_IN = os.path.join(ROOT, "tests", "golden", "taipei", "DSurfTomo.in")
+
+
+def _need_bin():
+    if not os.path.exists(BIN):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "dsurftomo_b200", "csrc"), "all"], check=True,
+                       capture_output=True)
+    assert os.path.exists(BIN)
+
+
+def test_driver_readers_match_python_mirror(tmp_path):
+    """DSurfTomo.in / data file / MOD parsed by the C++ driver == inputs.read_problem, bit for bit
+    (REAL*4 colatitude/longitude conversion, delsph distances, obst = dist / velocity)."""
+    _need_bin()
+    dump = tmp_path / "parsed.bin"
+    r = subprocess.run([BIN, TAIPEI_IN, "--outdir", str(tmp_path), "--parse-only", str(dump), "--quiet"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pb = inputs.read_problem(TAIPEI_IN)
+    raw = open(dump, "rb").read()
+    hdr = struct.unpack("12i", raw[:48])
+    fh = np.frombuffer(raw[48:96], np.float32)
+    (maxnar,) = struct.unpack("q", raw[96:104])
+    assert hdr == (pb.nx, pb.ny, pb.nz, pb.nsrc, pb.kmax, pb.dall, pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg,
+                   pb.maxiter, pb.ifsyn)
+    want = np.array([pb.goxd, pb.gozd, pb.dvxd, pb.dvzd, pb.weight, pb.damp, pb.minthk, pb.minvel, pb.maxvel,
+                     pb.spfra, pb.noiselevel, pb.threshold], np.float32)
+    assert np.array_equal(fh, want)
+    assert maxnar == pb.maxnar()
+    off = 104
+
+    def take(n, dt):
+        nonlocal off
+        a = np.frombuffer(raw[off:off + n * np.dtype(dt).itemsize], dt)
+        off += n * np.dtype(dt).itemsize
+        return a
+
+    for t in (pb.tRc, pb.tRg, pb.tLc, pb.tLg):
+        assert np.array_equal(take(len(t), np.float64), t)
+    for a in (pb.scxf, pb.sczf, pb.rcxf, pb.rczf):
+        assert np.array_equal(take(a.size, np.float32), a.ravel())
+    for a in (pb.periods, pb.wavetype, pb.igrt, pb.nrc1, pb.nsrc1):
+        assert np.array_equal(take(a.size, np.int32), a.ravel())
+    for a in (pb.obst, pb.dist, pb.depz, pb.vsf):
+        assert np.array_equal(take(a.size, np.float32), a.ravel())
+    assert off == len(raw)
+    log = open(tmp_path / "DSurfTomo.in.log").read().splitlines()
+    assert log[1].strip() == "S U R F  T O M O" and log[5] == "  25.20000 121.35000"  # '(2f10.5)'
+    assert log[9] == "   18   18    9"                                               # '(3i5)'
+    assert log[11] == "".join("%7.2f" % t for t in pb.tRc)                           # '(50f7.2)'
+
+
+def test_driver_list_directed_real_format():
+    """write(88,*) of REAL*4 (residualFirst/Last.dat, DWS line): gfortran prints G16.9E2-style items
+    separated by one blank; known outputs of `print *, x`."""
+    _need_bin()
+    vals = ["1", "0.1", "123.456", "1e-5", "1e10", "0", "-2.5", "31.5"]
+    r = subprocess.run([BIN, "--ld-real", *vals], capture_output=True, text=True)
+    got = [l[1:-1] for l in r.stdout.splitlines()]
+    assert got == ["   1.00000000    ", "  0.100000001    ", "   123.456001    ", "   9.99999975E-06",
+                   "   1.00000000E+10", "   0.00000000    ", "  -2.50000000    ", "   31.5000000    "]
+    assert all(float(g) == np.float32(v) for g, v in zip(got, vals))  # nine digits round-trip REAL*4
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_driver_fails_loudly_without_gpu(tmp_path):
+    _need_bin()
+    r = subprocess.run([BIN, TAIPEI_IN, "--outdir", str(tmp_path), "--maxiter", "1", "--quiet"],
+                       capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def _read_model_file(path, pb):
+    a = np.loadtxt(path)
+    assert a.shape == ((pb.nx - 2) * (pb.ny - 2) * (pb.nz - 1), 4)
+    return a
+
+
+@pytest.mark.gpu
+def test_driver_two_outer_iterations_match_oracle_chain(taipei, tmp_path):
+    _need_bin()
+    pb = taipei
+    r = subprocess.run([BIN, TAIPEI_IN, "--outdir", str(tmp_path), "--maxiter", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "Program finishes successfully" in r.stdout and " 2th iteration..." in r.stdout
+    # oracle chain
+    vs = pb.vsf.copy()
+    models, first = [], None
+    for it in range(2):
+        ref = O.calsurfg(pb, vels=vs, nthreads=8, mode=1)
+        s = hostglue.host_glue(pb, ref["dsurf"], ref["row"], ref["col"], ref["rw"])
+        if it == 0:
+            first = (ref["dsurf"].copy(), s["datweight"].copy())
+        L = O.lsmr(s["m"], s["n"], O.pack_iw(s["rows"], s["cols"]), s["vals"], s["cbst"], pb.damp)
+        vs, _ = hostglue.model_update(pb, vs, L["x"])
+        models.append(vs.copy())
+    lon = pb.gozd + np.arange(pb.ny - 2) * pb.dvzd
+    lat = pb.goxd - np.arange(pb.nx - 2) * pb.dvxd
+    for it, name in ((0, "DSurfTomo.inMeasure.dat.iter001"), (1, "DSurfTomo.inMeasure.dat.iter002"),
+                     (1, "DSurfTomo.inMeasure.dat")):
+        a = _read_model_file(tmp_path / name, pb)
+        want = models[it][: pb.nz - 1, 1:-1, 1:-1]                       # [k][j][i], i fastest in the file
+        got = a[:, 3].reshape(pb.nz - 1, pb.ny - 2, pb.nx - 2)
+        assert np.abs(got / want - 1).max() <= 1e-5 + 6e-6                # 1e-5 parity + '(f10.5)' rounding
+        assert np.allclose(a[: pb.nx - 2, 1], lat, atol=6e-6) and np.allclose(a[:: pb.nx - 2, 0][: pb.ny - 2], lon, atol=6e-6)
+        assert np.allclose(a[:: (pb.nx - 2) * (pb.ny - 2), 2], pb.depz[: pb.nz - 1], atol=6e-6)
+    # residualFirst.dat: dist, dsyn, obst, dsyn*w, obst*w, w  (main.f90:396-403)
+    res = np.loadtxt(tmp_path / "residualFirst.dat")
+    assert res.shape == (pb.dall, 6)
+    assert np.array_equal(res[:, 0].astype(np.float32), pb.dist) and np.array_equal(res[:, 2].astype(np.float32), pb.obst)
+    assert np.abs(res[:, 1] / first[0] - 1).max() <= 1e-5
+    assert np.array_equal(res[:, 5].astype(np.float32), first[1])
+    assert os.path.exists(tmp_path / "residualLast.dat")
+    log = open(tmp_path / "DSurfTomo.in.log").read()
+    assert log.count("Maximum and Average DWS values:") == 2 and log.count("th iteration...") == 2
+    assert "min and max velocity variation" in log and "Program finishes successfully" in log
