@@ -63,6 +63,9 @@ def lib():
                  "dsurf_plan_reset_rows", "dsurf_lsmr_destroy"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.dsurf_plan_sweeps.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.dsurf_plan_set_raypath.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.dsurf_plan_raypath_count.argtypes = [C.c_void_p]
+    L.dsurf_plan_raypath_count.restype = C.c_int64
     L.dsurf_plan_num_sweeps.argtypes = [C.c_void_p, C.c_int, C.c_int]
     _lib = L
     return L

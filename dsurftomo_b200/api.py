@@ -238,6 +238,12 @@ class Plan:
         pv = _c(pv, F64)
         check(lib().dsurf_plan_set_map(self.h, C.c_int(type_), C.c_int(period0), ptr(pv, C.c_double)), "plan_set_map")
 
+    def set_raypath(self, file, max_points=0):
+        """Append the traced ray geometry of every later sweeps() call to `file` in the format of the
+        reference's raypath.out (CalSurfG.f90:2276-2283); file=None stops and closes."""
+        check(lib().dsurf_plan_set_raypath(self.h, file.encode() if file is not None else None,
+                                           C.c_int(max_points)), "plan_set_raypath")
+
     def reset_rows(self):
         check(lib().dsurf_plan_reset_rows(self.h), "plan_reset_rows")
 

@@ -16,7 +16,7 @@
 // mean/std of the residual, grid coordinates of the output files) is restated in float with the
 // reference's operand order; build with -ffp-contract=off.
 //
-//   dsurftomo_b200 [DSurfTomo.in] [--outdir DIR] [--maxiter K] [--seed S] [--quiet]
+//   dsurftomo_b200 [DSurfTomo.in] [--outdir DIR] [--maxiter K] [--seed S] [--raypath] [--quiet]
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -360,6 +360,7 @@ int main(int argc, char **argv) {
   Tee io;
   std::string outdir, dump;
   int maxiter_override = -1;
+  bool raypath = false;
   uint64_t seed = 20150131ull;
   in.inputfile = "DSurfTomo.in";
   for (int a = 1; a < argc; a++) {
@@ -368,6 +369,7 @@ int main(int argc, char **argv) {
     else if (s == "--maxiter" && a + 1 < argc) maxiter_override = std::atoi(argv[++a]);
     else if (s == "--seed" && a + 1 < argc) seed = std::strtoull(argv[++a], nullptr, 10);
     else if (s == "--quiet") io.quiet = true;
+    else if (s == "--raypath") raypath = true;  // raypath.out of the last iteration (CalSurfG.f90:2276-2283)
     else if (s == "--parse-only" && a + 1 < argc) dump = argv[++a];
     else if (s == "--ld-real") {  // formatter self-test: print the list-directed form of each value
       for (int k = a + 1; k < argc; k++) std::printf("[%s]\n", ld_real((float)std::atof(argv[k])).c_str());
@@ -461,7 +463,9 @@ int main(int argc, char **argv) {
     io.out(" computing sensitivity matrix...\n");
     check(dsurf_plan_dispersion(plan), "dispersion");
     check(dsurf_plan_reset_rows(plan), "reset_rows");
+    if (raypath && iter == in.maxiter) check(dsurf_plan_set_raypath(plan, outpath("raypath.out").c_str(), 0), "set_raypath");
     check(dsurf_plan_sweeps(plan, 0, ngather), "sweeps");
+    if (raypath && iter == in.maxiter) check(dsurf_plan_set_raypath(plan, nullptr, 0), "set_raypath");
     int rb = 0;
     check(dsurf_plan_download(plan, nullptr, nullptr, nullptr, dsyn.data(), &rb), "download");
     if (rb) io.out(" Warning: ray paths reached the model boundary (CalSurfG.f90:1447-1454)\n");

@@ -14,6 +14,8 @@
 // eikonal path.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -101,6 +103,12 @@ struct dsurf_plan {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evt0 = nullptr, evt1 = nullptr;
   double ms_sweeps_total = 0;
+  // optional ray-path export (raypath.out, CalSurfG.f90:2276-2283)
+  FILE *path_fh = nullptr;
+  int path_cap = 0;
+  long long path_rays = 0;
+  DevBuf<float2> path;
+  DevBuf<int> path_n;
   // device-resident host glue (glue.cu)
   DevBuf<float> g_obst, g_cbst, g_datw, g_sorted, g_sval;
   DevBuf<double> g_norm;
@@ -398,6 +406,7 @@ extern "C" int dsurf_plan_destroy(dsurf_plan *p) {
   if (!p) return DSURF_OK;
   for (auto &e : p->ev)
     if (e) cudaEventDestroy(e);
+  if (p->path_fh) fclose(p->path_fh);
   delete p;
   return DSURF_OK;
 }
@@ -527,6 +536,26 @@ extern "C" int dsurf_plan_set_map(dsurf_plan *p, int type, int period0, const do
   return DSURF_OK;
 }
 
+// Ray-path export: every later dsurf_plan_sweeps call appends the traced ray
+// geometry to `file` in the format of the reference's raypath.out.  file == NULL closes it.
+extern "C" int dsurf_plan_set_raypath(dsurf_plan *p, const char *file, int max_points) {
+  if (!p) return DSURF_ERR_BAD_ARG;
+  if (p->path_fh) fclose(p->path_fh);
+  p->path_fh = nullptr;
+  p->path_cap = 0;
+  if (!file) return DSURF_OK;
+  if (p->forward_only) return DSURF_ERR_BAD_ARG;  // subroutine synthetic traces no rays
+  p->path_fh = fopen(file, "w");
+  if (!p->path_fh) {
+    set_error(__FILE__, __LINE__, "cannot open the ray-path file for writing");
+    return DSURF_ERR_BAD_ARG;
+  }
+  p->path_cap = max_points > 0 ? max_points : 4 * (p->g.nnx + p->g.nnz);
+  p->path_rays = 0;
+  return DSURF_OK;
+}
+extern "C" int64_t dsurf_plan_raypath_count(const dsurf_plan *p) { return p ? p->path_rays : 0; }
+
 extern "C" int dsurf_plan_reset_rows(dsurf_plan *p) {
   if (!p) return DSURF_ERR_BAD_ARG;
   p->nar = 0;
@@ -542,6 +571,50 @@ extern "C" int dsurf_plan_num_sweeps(const dsurf_plan *p, int g0, int g1) {
 }
 extern "C" int64_t dsurf_plan_nar(const dsurf_plan *p) { return p ? p->nar : 0; }
 extern "C" int dsurf_plan_nrows(const dsurf_plan *p) { return p ? p->dall : 0; }
+
+// gfortran list-directed REAL*4 item: one separator blank + G16.9E2
+static void ld_real(char *buf, size_t n, float v) {
+  int e = 0;
+  if (v != 0.0f) {
+    char t[32];
+    snprintf(t, sizeof t, "%.8E", (double)v);
+    e = atoi(strchr(t, 'E') + 1);
+  }
+  if (e >= -1 && e < 9)
+    snprintf(buf, n, " %12.*f    ", 8 - e, (double)v);
+  else
+    snprintf(buf, n, " %16.8E", (double)v);
+}
+
+// raypath.out records of one batch, in the reference's order (gather, receiver): "# nrp" then nrp
+// lines "latitude longitude" in degrees, rayx = (pi/2 - rgx)*180/pi, rayz = rgz*180/pi in REAL*4
+// (CalSurfG.f90:2276-2283; consumer scripts/plotpath.py)
+static int write_paths(dsurf_plan *p, const std::vector<SweepDesc> &hsw, const std::vector<RayDesc> &hrays) {
+  const int nrays = (int)hrays.size(), cap = p->path_cap;
+  std::vector<int> hn(nrays);
+  std::vector<float2> hp((size_t)nrays * cap);
+  DS_CUDA(cudaMemcpy(hn.data(), p->path_n.p, nrays * sizeof(int), cudaMemcpyDeviceToHost));
+  DS_CUDA(cudaMemcpy(hp.data(), p->path.p, hp.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+  char a[40], b[40];
+  for (int r = 0; r < nrays; r++) {
+    if (!hsw[hrays[r].sweep].do_rays) continue;
+    if (hn[r] > cap) {
+      set_error(__FILE__, __LINE__, "ray-path export: a ray has more points than max_points");
+      return DSURF_ERR_CAPACITY;
+    }
+    fprintf(p->path_fh, " #%12d\n", hn[r]);
+    for (int j = 0; j < hn[r]; j++) {
+      const float2 q = hp[(size_t)r * cap + j];
+      const float rayx = (kPi / 2 - q.x) * 180.0f / kPi, rayz = q.y * 180.0f / kPi;
+      ld_real(a, sizeof a, rayx);
+      ld_real(b, sizeof b, rayz);
+      fprintf(p->path_fh, "%s%s\n", a, b);
+    }
+    p->path_rays++;
+  }
+  fflush(p->path_fh);
+  return DSURF_OK;
+}
 
 // runs one batch of sweeps (already described in hsw / hrays); assemble = false keeps fdm
 static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<RayDesc> &hrays,
@@ -607,8 +680,14 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
     bv.ristr = p->ristr.p;
     bv.hcap = p->hcap;
     cudaEventRecord(p->ev[2], st);
+    const bool want_paths = p->path_fh != nullptr && p->path_cap > 0;
+    if (want_paths && (p->path.reserve((size_t)nrays * p->path_cap) || p->path_n.reserve(nrays))) {
+      set_error(__FILE__, __LINE__, "cudaMalloc failed (ray-path export buffers)");
+      return DSURF_ERR_CUDA;
+    }
     DS_CHECK(launch_rays(st, p->g, p->d_sw.p, p->d_rays.p, nrays, p->veln_all.p, bv, p->dsurf.p, p->fdm.p,
-                         p->bbox.p, p->flags.p + 1, p->flags.p));
+                         p->bbox.p, p->flags.p + 1, p->flags.p, want_paths ? p->path.p : nullptr,
+                         want_paths ? p->path_n.p : nullptr, p->path_cap));
     if (launches) *launches += 1;
     cudaEventRecord(p->ev[3], st);
     if (assemble) {
@@ -623,6 +702,7 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
     p->ms[3] += ms;
     cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]);
     p->ms[4] += ms;
+    if (want_paths) DS_CHECK(write_paths(p, hsw, hrays));
   }
   return DSURF_OK;
 }

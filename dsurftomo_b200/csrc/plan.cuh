@@ -86,6 +86,6 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
 int eikonal_resident_sweeps();
 int launch_rays(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, const RayDesc *d_rays, int nrays,
                 const float *d_veln_all, BatchView bv, float *d_tt, float *d_fdm, int4 *d_bbox,
-                int *d_rbint, int *d_err);
+                int *d_rbint, int *d_err, float2 *d_path = nullptr, int *d_path_n = nullptr, int path_cap = 0);
 
 }  // namespace dsurf

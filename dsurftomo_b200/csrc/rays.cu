@@ -90,9 +90,16 @@ __global__ void __launch_bounds__(128)
 k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ rays, int nrays,
        const float *__restrict__ veln_all, BatchView bv, float *__restrict__ tt_out,
        float *__restrict__ fdm_all, int4 *__restrict__ bbox, int *__restrict__ rbint_flag,
-       int *__restrict__ err_flag) {
+       int *__restrict__ err_flag, float2 *__restrict__ path, int *__restrict__ path_n, int path_cap) {
   const int rid = blockIdx.x * blockDim.x + threadIdx.x;
   if (rid >= nrays) return;
+  // optional ray-geometry export (rgx/rgz of rpaths, the reference's raypath.out block :2276-2283)
+  int np = 0;
+  auto rec = [&](float x, float z) {
+    if (path && np < path_cap) path[(size_t)rid * path_cap + np] = make_float2(x, z);
+    np++;
+  };
+  if (path_n) path_n[rid] = 0;
   const RayDesc rd = rays[rid];
   const SweepDesc d = sw[rd.sweep];
   bbox[rid] = make_int4(1, 0, 1, 0);  // empty until the ray has been traced
@@ -168,6 +175,7 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
     return;
   }
   float rgx_j = rd.rcx, rgz_j = rd.rcz;
+  rec(rgx_j, rgz_j);  // rgx(1), rgz(1) = receiver (:1910-1911)
   int sw1 = 0;
   {
     const float e1 = (scx - rgx_j) * earth;
@@ -192,6 +200,7 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
   int ipzr = (int)((rd.rcz - gozr) / dnzr) + 1;
   int igref = alive_cell(ipxr, ipzr);
   if (sw1 == 0 && igref == 1 && ipxr == isx && ipzr == isz) sw1 = 1;
+  if (sw1 == 1) rec(scx, scz);  // nrp = 2 (:1919-1921, 1949-1951)
   // register cache of the 4x4 vertex accumulators
   float acc[16];
   int civz = -1000, civx = -1000;
@@ -262,6 +271,8 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
       ipz = nnz - 1;
       rb = 1;
     }
+    rec(rgx_n, rgz_n);            // rgx(j+1) after the boundary clamp (:2082-2101)
+    if (sw1 == 1) rec(scx, scz);  // rgx(j+2) = source, nrp = j+2 (:2042-2046, 2057-2061)
     // ---- Frechet derivatives (:2110-2265)
     const int ivx = (ipx - 1) / kGd + 1, ivz = (ipz - 1) / kGd + 1;
     const int ivxo = (ipxo - 1) / kGd + 1, ivzo = (ipzo - 1) / kGd + 1;
@@ -382,14 +393,15 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
   }
   bbox[rid] = make_int4(bz0, bz1, bx0, bx1);  // vertex index ranges (i: z, j: x), empty if bz1 < bz0
   if (rb) atomicExch(rbint_flag, 1);
+  if (path_n) path_n[rid] = np;
 }
 
 int launch_rays(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, const RayDesc *d_rays, int nrays,
                 const float *d_veln_all, BatchView bv, float *d_tt, float *d_fdm, int4 *d_bbox,
-                int *d_rbint, int *d_err) {
+                int *d_rbint, int *d_err, float2 *d_path, int *d_path_n, int path_cap) {
   if (nrays <= 0) return DSURF_OK;
   k_rays<<<(nrays + 127) / 128, 128, 0, st>>>(g, d_sw, d_rays, nrays, d_veln_all, bv, d_tt, d_fdm, d_bbox,
-                                              d_rbint, d_err);
+                                              d_rbint, d_err, d_path, d_path_n, path_cap);
   DS_CUDA(cudaGetLastError());
   return DSURF_OK;
 }

@@ -194,6 +194,14 @@ int dsurf_plan_nrows(const dsurf_plan *plan);
 /* download everything produced so far (any pointer may be NULL) */
 int dsurf_plan_download(dsurf_plan *plan, int *iw_rows /* nar */, float *rw, int *col, float *dsurf,
                         int *rbint);
+/* Ray-path export (optional debug output of the ray tracer; the reference's raypath.out block,
+ * CalSurfG.f90:2276-2283, consumer scripts/plotpath.py): every later dsurf_plan_sweeps call appends,
+ * per traced ray in (gather, receiver) order, a list-directed "# nrp" record and nrp records
+ * "latitude longitude" (degrees) from the receiver to the source.  max_points <= 0 selects
+ * 4*(nnx+nnz) points per ray; a longer ray makes dsurf_plan_sweeps return DSURF_ERR_CAPACITY.
+ * file == NULL stops the export and closes the file. */
+int dsurf_plan_set_raypath(dsurf_plan *plan, const char *file, int max_points);
+int64_t dsurf_plan_raypath_count(const dsurf_plan *plan);
 /* stage-level outputs for parity tests: last solved sweep of gather g, pass ig (1 or 2) */
 int dsurf_plan_debug_sweep(dsurf_plan *plan, int g, int ig, float *veln, float *ttn, float *ttnr,
                            int *nstsr, float *rgeom, float *fdm /* [nrc][nx][ny] or NULL */);

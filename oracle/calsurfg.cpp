@@ -84,6 +84,29 @@ extern "C" int oracle_sweep_rays(int nx, int ny, float goxd, float gozd, float d
   return 0;
 }
 
+// ray geometry of every receiver of one sweep: npts[nrc]; px/pz[nrc][cap] = rgx/rgz (radians)
+extern "C" int oracle_sweep_paths(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
+                                  const double *pv, float scx, float scz, int nrc, const float *rcx,
+                                  const float *rcz, int cap, int *npts, float *px, float *pz) {
+  Fmm f;
+  f.setup(nx, ny, goxd, gozd, dvxd, dvzd);
+  f.solve_source(pv, scx, scz);
+  if (f.error) return f.error;
+  std::vector<float> fdm((size_t)(f.nvz + 2) * (f.nvx + 2)), x, z;
+  f.path_x = &x;
+  f.path_z = &z;
+  for (int r = 0; r < nrc; r++) {
+    f.rpaths(scx, scz, fdm.data(), rcx[r], rcz[r]);
+    if (f.error) return f.error;
+    npts[r] = (int)x.size();
+    for (int j = 0; j < (int)x.size() && j < cap; j++) {
+      px[(size_t)r * cap + j] = x[j];
+      pz[(size_t)r * cap + j] = z[j];
+    }
+  }
+  return 0;
+}
+
 namespace {
 // gather loop of CalSurfG (:1135-1456) on given dispersion results.  pv[t] / sen[t][q] per type
 // t = Rc,Rg,Lc,Lg (pv of Rc/Lc have kmax columns, see :1003-1004), q = vs,vp,rho.

@@ -604,6 +604,11 @@ void Fmm::rpaths(float scx, float scz, float *fdm, float surfrcx, float surfrcz)
     return;
   }
   float rgx_j = surfrcx, rgz_j = surfrcz;  // rgx(j), rgz(j)
+  auto rec = [&](float x, float z) {
+    if (path_x) path_x->push_back(x), path_z->push_back(z);
+  };
+  if (path_x) path_x->clear(), path_z->clear();
+  rec(rgx_j, rgz_j);  // rgx(1) = receiver, :1910-1911
   float e1 = (scx - rgx_j) * earth;
   float sred = e1 * e1;
   float e2 = (scz - rgz_j) * earth * std::sin(rgx_j);
@@ -631,6 +636,7 @@ void Fmm::rpaths(float scx, float scz, float *fdm, float surfrcx, float surfrcz)
       if (ipx == isx && ipz == isz) sw = 1;
     }
   }
+  if (sw == 1) rec(scx, scz);  // rgx(2) = source, nrp = 2, :1919-1921 / :1949-1961
   for (long j = 1; j <= maxrp; j++) {
     if (sw == 1) break;
     float dtx, dtz;
@@ -705,6 +711,8 @@ void Fmm::rpaths(float scx, float scz, float *fdm, float surfrcx, float surfrcz)
       ipz = nnz - 1;
       rbint = 1;
     }
+    rec(rgx_n, rgz_n);           // rgx(j+1) as left by the boundary clamp
+    if (sw == 1) rec(scx, scz);  // rgx(j+2) = source, nrp = j+2, :2042-2046 / :2057-2071
     // ---- Frechet derivatives, :2110-2265
     const int ivx = (ipx - 1) / gdx + 1;
     const int ivz = (ipz - 1) / gdz + 1;

@@ -50,6 +50,9 @@ struct Fmm {
   void solve_source(const double *pv, float x, float z);
   float srtimes(float scx, float scz, float rcx1, float rcz1);                      // :1636-1759
   void rpaths(float scx, float scz, float *fdm, float surfrcx, float surfrcz);      // :1771-2318
+  // ray geometry rgx(1:nrp), rgz(1:nrp) of the last rpaths call when non-null (what the
+  // commented raypath.out block :2276-2283 would print)
+  std::vector<float> *path_x = nullptr, *path_z = nullptr;
 };
 
 }  // namespace oracle

@@ -57,6 +57,13 @@ int oracle_sweep_rays(int nx, int ny, float goxd, float gozd, float dvxd, float 
                       const double *pv, float scx, float scz, int nrc, const float *rcx,
                       const float *rcz, float *tt, float *fdm);
 
+/* Ray geometry rgx/rgz(1:nrp) (colatitude, longitude in radians, receiver first, source last) of
+ * every receiver of one sweep -- the content of the reference's raypath.out block
+ * (CalSurfG.f90:2276-2283).  npts[nrc]; px, pz are [nrc][cap]. */
+int oracle_sweep_paths(int nx, int ny, float goxd, float gozd, float dvxd, float dvzd,
+                       const double *pv, float scx, float scz, int nrc, const float *rcx,
+                       const float *rcz, int cap, int *npts, float *px, float *pz);
+
 /* CalSurfG.f90:939-1459; same argument list as the Fortran subroutine (by value where
  * scalar).  nthreads: OpenMP threads; mode 0 = reference-faithful threading (dispersion
  * only), 1 = additionally thread the independent gathers.  Returns 0 or an error code

@@ -129,6 +129,23 @@ def sweep_rays(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, rcx, rcz):
     return err, tt, fdm
 
 
+def sweep_paths(nx, ny, goxd, gozd, dvxd, dvzd, pv, scx, scz, rcx, rcz, cap=4096):
+    """Ray geometry (colatitude, longitude in radians) per receiver: list of (n,2) arrays."""
+    pv = np.ascontiguousarray(pv, np.float64)
+    rcx = np.ascontiguousarray(rcx, np.float32)
+    rcz = np.ascontiguousarray(rcz, np.float32)
+    nrc = len(rcx)
+    npts = np.zeros(nrc, np.int32)
+    px = np.zeros((nrc, cap), np.float32)
+    pz = np.zeros((nrc, cap), np.float32)
+    err = lib().oracle_sweep_paths(
+        C.c_int(nx), C.c_int(ny), C.c_float(goxd), C.c_float(gozd), C.c_float(dvxd), C.c_float(dvzd),
+        _p(pv, C.c_double), C.c_float(scx), C.c_float(scz), C.c_int(nrc), _p(rcx, C.c_float),
+        _p(rcz, C.c_float), C.c_int(cap), _p(npts, C.c_int), _p(px, C.c_float), _p(pz, C.c_float))
+    assert err == 0 and npts.max() <= cap
+    return [np.stack([px[r, : npts[r]], pz[r, : npts[r]]], axis=1) for r in range(nrc)]
+
+
 def calsurfg(pb, vels=None, nthreads=1, mode=0, maxnar=None):
     """Run the oracle CalSurfG on a Problem.  Returns dict(dsurf, rw, row, col, nar, ...)."""
     vels = np.ascontiguousarray(pb.vsf if vels is None else vels, np.float32)

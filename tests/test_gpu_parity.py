@@ -451,3 +451,49 @@ def test_full_size_rows_match_oracle_and_normal_equations(cfg3_slice):
     g = A.T @ (A @ x - s["cbst"].astype(np.float64)) + pb.damp ** 2 * x
     assert np.linalg.norm(g) <= 1e-4 * np.linalg.norm(A.T @ s["cbst"].astype(np.float64))
     plan.close()
+
+
+def test_raypath_export_matches_oracle(taipei, tmp_path):
+    """ray-path export in the reference's raypath.out format (CalSurfG.f90:2276-2283):
+    '# nrp' + nrp 'latitude longitude' records per traced ray, receiver first, source last.  With the
+    same velocity map the geometry is bit-identical to the oracle's rgx/rgz."""
+    pb = taipei
+    plan = api.Plan(pb)
+    plan.dispersion()
+    pv_all = plan.get_dispersion(0)[0]  # [period][nx*ny] maps the sweeps propagate through (Rc only)
+    f = tmp_path / "raypath.out"
+    g0, g1 = 3, 9
+    plan.set_raypath(str(f))
+    plan.reset_rows()
+    plan.sweeps(g0, g1)
+    plan.set_raypath(None)
+    lines = open(f).read().splitlines()
+    pi = np.float32(3.1415926535898)
+    cum = np.concatenate([[0], np.cumsum(pb.nsrc1)])
+    pos = 0
+    nrays = 0
+    for g in range(g0, g1):
+        k = int(np.searchsorted(np.cumsum(pb.nsrc1), g, side="right"))
+        s = g - int(cum[k])
+        nrc = int(pb.nrc1[k, s])
+        ref = O.sweep_paths(pb.nx, pb.ny, pb.goxd, pb.gozd, pb.dvxd, pb.dvzd, pv_all[pb.periods[k, s] - 1],
+                            pb.scxf[k, s], pb.sczf[k, s], pb.rcxf[k, s, :nrc], pb.rczf[k, s, :nrc])
+        for p in ref:
+            hdr = lines[pos].split()
+            assert hdr[0] == "#" and int(hdr[1]) == len(p) and len(lines[pos]) == 14  # ' #' + I12
+            got = np.array([[np.float32(v) for v in l.split()] for l in lines[pos + 1: pos + 1 + len(p)]], np.float32)
+            want_lat = (pi / np.float32(2) - p[:, 0]) * np.float32(180.0) / pi
+            want_lon = p[:, 1] * np.float32(180.0) / pi
+            assert np.array_equal(got[:, 0], want_lat) and np.array_equal(got[:, 1], want_lon)
+            assert all(len(l) == 34 for l in lines[pos + 1: pos + 1 + len(p)])        # two list-directed REAL*4
+            pos += 1 + len(p)
+            nrays += 1
+    assert pos == len(lines) and nrays > 0
+    # the export does not disturb the rows: same COO as a run without it
+    with_paths = plan.download()
+    with_paths = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in with_paths.items()}
+    plan.reset_rows()
+    plan.sweeps(g0, g1)
+    plain = plan.download()
+    assert with_paths["nar"] == plain["nar"] and np.array_equal(with_paths["rw"], plain["rw"])
+    plan.close()

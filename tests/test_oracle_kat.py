@@ -269,3 +269,27 @@ def test_taipei_two_outer_iterations_reduce_misfit(taipei):
         vs, _ = hostglue.model_update(pb, vs, L["x"])
         assert vs.min() >= pb.minvel - 1e-6 and vs.max() <= pb.maxvel + 1e-6
     assert stds[1] < stds[0]
+
+
+def test_ray_geometry_uniform_medium(taipei):
+    """Ray geometry (the reference's raypath.out content, CalSurfG.f90:2276-2283) in a uniform medium:
+    starts at the receiver, ends exactly at the source, steps of ~dpl = half the smallest cell edge,
+    distance to the source decreases monotonically, total length ~ great-circle distance."""
+    pb = taipei
+    k, s = 10, 1
+    nrc = int(pb.nrc1[k, s])
+    sx, sz = pb.scxf[k, s], pb.sczf[k, s]
+    paths = O.sweep_paths(pb.nx, pb.ny, pb.goxd, pb.gozd, pb.dvxd, pb.dvzd, _uniform(pb, 1.25), sx, sz,
+                          pb.rcxf[k, s, :nrc], pb.rczf[k, s, :nrc])
+    assert len(paths) == nrc
+    pi = np.float32(3.1415926535898)
+    dpl = 0.5 * min(pb.dvxd, pb.dvzd * np.sin(np.radians(90 - pb.goxd))) * float(pi) / 180.0 / 8 * 6371.0
+    for r, p in enumerate(paths):
+        assert p[0, 0] == pb.rcxf[k, s, r] and p[0, 1] == pb.rczf[k, s, r]
+        assert p[-1, 0] == sx and p[-1, 1] == sz
+        d = np.array([float(inputs.delsph(sx, sz, x, z)) for x, z in p])
+        assert np.all(np.diff(d[:-1]) < 0)
+        seg = np.array([float(inputs.delsph(p[i, 0], p[i, 1], p[i + 1, 0], p[i + 1, 1])) for i in range(len(p) - 2)])
+        if len(seg):
+            assert np.abs(seg / dpl - 1).max() < 0.05
+        assert abs((seg.sum() + d[-2]) / d[0] - 1) < 0.02
