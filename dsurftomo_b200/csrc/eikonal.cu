@@ -917,7 +917,7 @@ __device__ __forceinline__ int find_in_smem(const int2 *sm, int lim, int nid, in
   return found;
 }
 
-// LAZY back-pointers (default): a node's status word holds its heap slot exactly only while the slot
+// LAZY back-pointers (optional, DSURF_EIKONAL_LAZY=1): a node's status word holds its heap slot exactly only while the slot
 // lies in the global part of the heap (slot >= HS).  Moves between two shared-memory slots -- every
 // level of a sift-down above the slab, most sift-ups -- do not touch the node array at all; a stored
 // value in [1, HS) therefore only says "somewhere in the shared-memory part", and the slot is found
@@ -925,6 +925,8 @@ __device__ __forceinline__ int find_in_smem(const int2 *sm, int lim, int nid, in
 // r01_launches_v3_summary.md): the eager scheme's scattered 4-byte status stores are half of the
 // kernel's store sectors, each a read-modify-write of a 32-byte DRAM sector at full occupancy.
 // Pop order and arithmetic are unchanged (heap contents are identical; only the inverse map is lazy).
+// Result on B200 (gpurun_out/s8_eik_*.json, cfg 3 type-block steps): 882 sweeps/s lazy vs 939 eager -- the
+// DRAM sectors saved do not pay for the slot searches because the kernel is issue-bound, not DRAM-bound.
 template <bool REFINED, int kG, bool LAZY>
 __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int ntr, int hcap, int gl, unsigned gm,
                       int gbase, unsigned wmask, int vnl, int vnr, int vnt, int vnb) {
@@ -1441,7 +1443,9 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     const int ng = g8 ? V3<8>::NG : V3<16>::NG;
     const int hs = g8 ? V3<8>::HS : V3<16>::HS;
     const size_t smem = (size_t)kWarpsPerBlock * ng * (hs + kScr) * sizeof(int2);
-    static const bool eager = getenv("DSURF_EIKONAL_EAGER") != nullptr;  // A/B: eager heap back-pointers
+    // lazy heap back-pointers (see march3): measured 6 % SLOWER than the eager scheme at cfg 3 (the kernel is
+    // issue-bound, and a slot search by one sweep of a warp stalls the other), so eager is the default
+    static const bool eager = getenv("DSURF_EIKONAL_LAZY") == nullptr;
     static bool attr3 = false;
     if (!attr3) {
       const int s8 = (int)((size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2));

@@ -669,76 +669,177 @@ k_fused_beta(LsmrScalars *S, const double *partial, int np, const double *extra,
 // local reorthogonalisation (modified Gram-Schmidt against the stored window), alpha = ||v||,
 // plane rotations, v/h/hbar/x updates, ||x|| and the stopping tests (lsmrModule.f90:498-616, 731-748):
 // k_reorth x (localVecs+1) + k_rotations + k_update + k_tests in one launch.  CTA `rank` owns elements
-// [rank*chunk, min(n, (rank+1)*chunk)) and keeps its slice of v in shared memory.
+// [rank*chunk, min(n, (rank+1)*chunk)).  The Gram-Schmidt steps are serial (each dot product needs the
+// previous subtraction), so what matters is the latency of one step: with <= kEPT elements per thread
+// the slice of v and two window vectors live in REGISTERS and the next window vector is prefetched
+// while the current dot product is being reduced; larger slices keep v in shared memory.
+constexpr int kEPT = 10;
+
+struct TailShared {
+  double wsum[33];
+  double red[2][kClMax];
+  float bc[4];
+  int bflag;
+};
+
+// rank 0 / thread 0: alpha, rotations, broadcast block for the update phase
+__device__ __forceinline__ void tail_scalars(LsmrScalars *S, bool bp, double sumv2, float damp, TailShared &sh) {
+  if (bp) {  // alpha = ||v|| after the last subtraction (lsmrModule.f90:503)
+    const float a = (float)sqrt(sumv2);
+    S->alpha = a;
+    S->inv_alpha = a > 0.0f ? 1.0f / a : 1.0f;
+    S->alpha_pos = a > 0.0f;
+  }
+  rotations_scalar(S, damp);
+  sh.bc[0] = S->inv_alpha;
+  sh.bc[1] = S->f1;
+  sh.bc[2] = S->f2;
+  sh.bc[3] = S->f3;
+  sh.bflag = (S->beta_pos && S->alpha_pos) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
-k_fused_tail(LsmrScalars *S, float *v, const float *localV, float *h, float *hbar, float *x, int n, int chunk,
-             float damp, float atol, float btol, float ctol, int itnlim, int force_iters) {
+k_fused_tail(LsmrScalars *S, float *__restrict__ v, const float *__restrict__ localV, float *__restrict__ h,
+             float *__restrict__ hbar, float *__restrict__ x, int n, int chunk, float damp, float atol, float btol,
+             float ctol, int itnlim, int force_iters) {
   extern __shared__ float vs[];
-  __shared__ double wsum[33];
-  __shared__ double red[2][kClMax];
-  __shared__ float bc[4];
-  __shared__ int bflag;
+  __shared__ TailShared sh;
   cg::cluster_group cl = cg::this_cluster();
   if (S->stop) return;  // uniform over the cluster
   const int rank = (int)cl.block_rank(), tid = threadIdx.x;
   const int i0 = min(n, rank * chunk), cnt = min(n, i0 + chunk) - i0;
   const bool bp = S->beta_pos != 0;
   const int lim = S->orthoLimit;
-  for (int j = tid; j < cnt; j += kFusedThreads) vs[j] = v[i0 + j];
-  __syncthreads();
   int buf = 0;
   double tot = 0.0;
+  if (chunk <= kEPT * kFusedThreads) {
+    // ------------------------------------------------ register path
+    float vr[kEPT], qa[kEPT], qb[kEPT];
+    bool ok[kEPT];
+#pragma unroll
+    for (int u = 0; u < kEPT; u++) {
+      const int j = tid + u * kFusedThreads;
+      ok[u] = j < cnt;
+      vr[u] = ok[u] ? v[i0 + j] : 0.0f;
+      qa[u] = 0.0f;
+      qb[u] = (bp && lim > 0 && ok[u]) ? localV[i0 + j] : 0.0f;  // q_0
+    }
+    if (bp) {
+      float dprev = 0.0f;
+      for (int c = 0; c <= lim; c++) {
+        // here: qa = q_{c-1} (c > 0), qb = q_c (c < lim)
+        double acc = 0.0;
+        const bool more = c + 1 < lim;
+        const float *qn = localV + (size_t)(c + 1) * n + i0;
+#pragma unroll
+        for (int u = 0; u < kEPT; u++) {
+          if (c > 0) vr[u] = vr[u] - dprev * qa[u];
+          qa[u] = (more && ok[u]) ? qn[tid + u * kFusedThreads] : 0.0f;  // prefetch q_{c+1}; lands during the reduction
+        }
+#pragma unroll
+        for (int u = 0; u < kEPT; u++) {
+          acc += (c < lim) ? (double)vr[u] * (double)qb[u] : (double)vr[u] * (double)vr[u];
+        }
+        tot = cluster_sum(cl, cta_sum(acc, sh.wsum), sh.red[buf]);
+        buf ^= 1;
+        dprev = (float)tot;
+#pragma unroll
+        for (int u = 0; u < kEPT; u++) {  // rotate: q_c becomes "previous", the prefetched q_{c+1} "current"
+          const float t = qa[u];
+          qa[u] = qb[u];
+          qb[u] = t;
+        }
+      }
+    }
+    if (rank == 0 && tid == 0) tail_scalars(S, bp, tot, damp, sh);
+    // h, hbar, x of this thread: issued before the barrier, consumed after it
+    float hr[kEPT], hbr[kEPT], xr[kEPT];
+#pragma unroll
+    for (int u = 0; u < kEPT; u++) {
+      const int i = i0 + tid + u * kFusedThreads;
+      hr[u] = ok[u] ? h[i] : 0.0f;
+      hbr[u] = ok[u] ? hbar[i] : 0.0f;
+      xr[u] = ok[u] ? x[i] : 0.0f;
+    }
+    cl.sync();
+    const float *bc0 = cl.map_shared_rank(sh.bc, 0);
+    const float ia = bc0[0], f1 = bc0[1], f2 = bc0[2], f3 = bc0[3];
+    const bool scale_v = *cl.map_shared_rank(&sh.bflag, 0) != 0;
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < kEPT; u++) {
+      if (ok[u]) {
+        const int i = i0 + tid + u * kFusedThreads;
+        float vi = vr[u];
+        if (scale_v) vi = ia * vi;
+        v[i] = vi;
+        const float hb = hr[u] - f1 * hbr[u];
+        hbar[i] = hb;
+        const float xi = xr[u] + f2 * hb;
+        x[i] = xi;
+        h[i] = vi - f3 * hr[u];
+        acc += (double)xi * (double)xi;
+      }
+    }
+    tot = cluster_sum(cl, cta_sum(acc, sh.wsum), sh.red[buf]);  // also keeps rank 0's smem alive until all have read it
+    if (rank == 0 && tid == 0) tests_scalar(S, tot, atol, btol, ctol, itnlim, force_iters);
+    return;
+  }
+  // -------------------------------------------------- shared-memory path (large n)
+  for (int j = tid; j < cnt; j += kFusedThreads) vs[j] = v[i0 + j];
+  __syncthreads();
   if (bp) {
     float dprev = 0.0f;
     for (int c = 0; c <= lim; c++) {
       const float *qp = (c > 0) ? localV + (size_t)(c - 1) * n + i0 : nullptr;
       const float *qc = (c < lim) ? localV + (size_t)c * n + i0 : nullptr;
       double acc = 0.0;
-      for (int j = tid; j < cnt; j += kFusedThreads) {
-        float vi = vs[j];
-        if (qp) {
-          vi = vi - dprev * qp[j];
-          vs[j] = vi;
+      for (int j0 = tid; j0 < cnt; j0 += 4 * kFusedThreads) {
+        float a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // all loads of the unrolled group in flight together
+          const int j = j0 + u * kFusedThreads;
+          a[u] = (qp && j < cnt) ? qp[j] : 0.0f;
+          b[u] = (qc && j < cnt) ? qc[j] : 0.0f;
         }
-        acc += qc ? (double)vi * (double)qc[j] : (double)vi * (double)vi;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u * kFusedThreads;
+          if (j < cnt) {
+            float vi = vs[j];
+            if (qp) {
+              vi = vi - dprev * a[u];
+              vs[j] = vi;
+            }
+            acc += qc ? (double)vi * (double)b[u] : (double)vi * (double)vi;
+          }
+        }
       }
-      tot = cluster_sum(cl, cta_sum(acc, wsum), red[buf]);
+      tot = cluster_sum(cl, cta_sum(acc, sh.wsum), sh.red[buf]);
       buf ^= 1;
       dprev = (float)tot;
     }
   }
-  if (rank == 0 && tid == 0) {
-    if (bp) {  // alpha = ||v|| after the last subtraction (lsmrModule.f90:503)
-      const float a = (float)sqrt(tot);
-      S->alpha = a;
-      S->inv_alpha = a > 0.0f ? 1.0f / a : 1.0f;
-      S->alpha_pos = a > 0.0f;
-    }
-    rotations_scalar(S, damp);
-    bc[0] = S->inv_alpha;
-    bc[1] = S->f1;
-    bc[2] = S->f2;
-    bc[3] = S->f3;
-    bflag = (S->beta_pos && S->alpha_pos) ? 1 : 0;
-  }
+  if (rank == 0 && tid == 0) tail_scalars(S, bp, tot, damp, sh);
   cl.sync();
-  const float *bc0 = cl.map_shared_rank(bc, 0);
+  const float *bc0 = cl.map_shared_rank(sh.bc, 0);
   const float ia = bc0[0], f1 = bc0[1], f2 = bc0[2], f3 = bc0[3];
-  const bool scale_v = *cl.map_shared_rank(&bflag, 0) != 0;
+  const bool scale_v = *cl.map_shared_rank(&sh.bflag, 0) != 0;
   double acc = 0.0;
   for (int j = tid; j < cnt; j += kFusedThreads) {
     const int i = i0 + j;
     float vi = vs[j];
     if (scale_v) vi = ia * vi;
     v[i] = vi;
-    const float hb = h[i] - f1 * hbar[i];
+    const float hi = h[i];
+    const float hb = hi - f1 * hbar[i];
     hbar[i] = hb;
     const float xi = x[i] + f2 * hb;
     x[i] = xi;
-    h[i] = vi - f3 * h[i];
+    h[i] = vi - f3 * hi;
     acc += (double)xi * (double)xi;
   }
-  tot = cluster_sum(cl, cta_sum(acc, wsum), red[buf]);  // also keeps rank 0's smem alive until all have read it
+  tot = cluster_sum(cl, cta_sum(acc, sh.wsum), sh.red[buf]);
   if (rank == 0 && tid == 0) tests_scalar(S, tot, atol, btol, ctol, itnlim, force_iters);
 }
 
@@ -1216,6 +1317,7 @@ extern "C" int dsurf_lsmr_destroy(dsurf_lsmr_sys *sys) {
   return DSURF_OK;
 }
 extern "C" int64_t dsurf_lsmr_nnz(const dsurf_lsmr_sys *sys) { return sys ? sys->nnz : 0; }
+extern "C" int dsurf_lsmr_fused_cluster(const dsurf_lsmr_sys *sys) { return sys ? sys->fused_cl : 0; }
 extern "C" int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *comm, int rank, int nranks) {
   if (!sys) return DSURF_ERR_BAD_ARG;
   sys->comm = comm;
@@ -1232,7 +1334,7 @@ static void choose_fused(dsurf_lsmr_sys *s) {
   if (getenv("DSURF_LSMR_NO_FUSE") != nullptr) return;
   for (int cl : {16, 8}) {
     const int chunk = (s->n_int + cl - 1) / cl;
-    const size_t smem = (size_t)chunk * sizeof(float);
+    const size_t smem = chunk <= kEPT * kFusedThreads ? 0 : (size_t)chunk * sizeof(float);  // register path needs none
     if (smem > 200 * 1024) continue;
     if (cl > 8 && (cudaFuncSetAttribute(k_fused_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
                    cudaFuncSetAttribute(k_fused_beta, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {

@@ -253,6 +253,9 @@ int dsurf_lsmr_solve(dsurf_lsmr_sys *sys, float damp, float atol, float btol, fl
                      float *normA, float *condA, float *normr, float *normAr, float *normx,
                      double *ms_total, double *ms_spmv, double *ms_spmtv);
 int64_t dsurf_lsmr_nnz(const dsurf_lsmr_sys *sys);
+/* CTAs of the thread-block cluster running the fused small-vector phases of the last solve
+ * (16 or 8), 0 = unfused kernels, -1 = no solve yet */
+int dsurf_lsmr_fused_cluster(const dsurf_lsmr_sys *sys);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,8 @@ def main():
     nnz = len(V)
     bytes_it = 16 * nnz + 8 * (m + 1) + 12 * m + 80 * n
     it_s = best["itn"] / (best["ms_total"] / 1e3)
-    out = dict(fused=os.environ.get("DSURF_LSMR_NO_FUSE") is None, fork=os.environ.get("DSURF_LSMR_NO_FORK") is None,
+    from dsurftomo_b200._lib import lib
+    out = dict(fused=os.environ.get("DSURF_LSMR_NO_FUSE") is None, fused_cluster=int(lib().dsurf_lsmr_fused_cluster(sysl.h)), fork=os.environ.get("DSURF_LSMR_NO_FORK") is None,
                m=m, n=n, nnz=nnz, iters=best["itn"], iters_per_s=it_s, us_per_iter=1e6 / it_s,
                b_lsmr_gbs=bytes_it * it_s / 1e9, spmv_us=best["ms_spmv"] * 1e3 / best["itn"],
                spmtv_us=best["ms_spmtv"] * 1e3 / best["itn"], normx=best["normx"], normr=best["normr"],

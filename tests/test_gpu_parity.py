@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
+from conftest import ROOT
 from dsurftomo_b200 import api, hostglue, inputs
 
 pytestmark = pytest.mark.gpu
@@ -324,7 +325,7 @@ def test_device_glue_matches_host_glue(taipei):
     assert np.array_equal(second["rw"], ref2["rw"])
 
 
-@pytest.mark.parametrize("var", ["DSURF_EIKONAL_V1", "DSURF_EIKONAL_V2"])
+@pytest.mark.parametrize("var", ["DSURF_EIKONAL_V1", "DSURF_EIKONAL_V2", "DSURF_EIKONAL_LAZY"])
 def test_reference_eikonal_variants_also_bit_exact(var):
     """The simple (v1: one warp per sweep), overlapped (v2) and sub-warp (v3, default: 8 lanes per
     sweep) marches must all reproduce the oracle; v1/v2 are selected by an environment variable at
@@ -497,3 +498,35 @@ def test_raypath_export_matches_oracle(taipei, tmp_path):
     plain = plan.download()
     assert with_paths["nar"] == plain["nar"] and np.array_equal(with_paths["rw"], plain["rw"])
     plan.close()
+
+
+def test_lsmr_fused_cluster_kernels_match_unfused(taipei):
+    """The fused small-vector phases (one thread-block cluster: k_fused_beta / k_fused_tail, register path)
+    against the unfused kernel sequence (DSURF_LSMR_NO_FUSE=1, separate process): same iteration count
+    and stopping reason, solution equal to fp32 rounding of differently ordered fp64 partial sums."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from dsurftomo_b200 import api, inputs, hostglue\n"
+        "from dsurftomo_b200._lib import lib\n"
+        "pb = inputs.config(1)\n"
+        "plan = api.Plan(pb); plan.dispersion(); plan.reset_rows(); plan.sweeps()\n"
+        "sysd = api.LsmrSystem.from_plan(plan)\n"
+        "r = sysd.solve(pb.damp)\n"
+        "print(json.dumps(dict(cl=int(lib().dsurf_lsmr_fused_cluster(sysd.h)), itn=r['itn'], istop=r['istop'],"
+        " normr=r['normr'], x=r['x'].tolist())))\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    out = {}
+    for name, extra in (("fused", {}), ("unfused", {"DSURF_LSMR_NO_FUSE": "1"})):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["fused"]["cl"] in (8, 16) and out["unfused"]["cl"] == 0
+    assert out["fused"]["itn"] == out["unfused"]["itn"] and out["fused"]["istop"] == out["unfused"]["istop"]
+    xf, xu = np.array(out["fused"]["x"]), np.array(out["unfused"]["x"])
+    assert np.abs(xf - xu).max() <= 1e-6 * np.abs(xu).max()
