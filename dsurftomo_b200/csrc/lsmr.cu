@@ -15,6 +15,7 @@
 // Bound: HBM bandwidth.  Algorithmic bytes per iteration:
 //   16*nnz + 8*(m+1) + 12*m + 80*n.
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <vector>
 #include "../../include/dsurftomo_b200.h"
 #include <cooperative_groups.h>
@@ -275,6 +276,167 @@ k_bspmv_cols(const long long *__restrict__ ptr, const int *__restrict__ row, con
       __syncthreads();
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent long-row / long-column products (depth-blocked layout).  ncu of the one-warp-per-row
+// kernels above (profiles/r01_lsmr_iter_kernels.md): 3.1 TB/s (rows) and 2.35 TB/s (columns) of DRAM
+// reads, long-scoreboard stalls 20-28 per issue -- every warp lived for one row only, i.e. spent its
+// life in the dependent chain rowlist -> ptr -> pos -> x and in the block-wide partial-sum barrier.
+// Here a fixed grid of warps strides over the row list: the next row's descriptor is fetched while
+// the current row streams, four 36-byte blocks per lane are in flight at once, and the block-level
+// sum of squares is reduced once per CTA.  The column list is sorted by length (longest first), so
+// the grid-stride assignment is balanced.  Row r is always handled by warp (r mod #warps): the
+// summation order, and therefore the result, is fixed for a given device.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPersistBlocksPerSM = 4;
+
+__global__ void __launch_bounds__(kSpmvWarps * 32, kPersistBlocksPerSM)
+k_bspmv_rows_p(const long long *__restrict__ ptr, const int *__restrict__ pos, const float4 *__restrict__ val,
+               const float4 *__restrict__ x4, float *__restrict__ y, const float *__restrict__ scale_ptr,
+               float scale_sign, const int *__restrict__ rowlist, int nrows, double *__restrict__ partial,
+               const int *__restrict__ stop) {
+  __shared__ double sh[kSpmvWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = gridDim.x * kSpmvWarps;
+  double sq = 0.0;
+  if (stop == nullptr || *stop == 0) {
+    const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
+    int wi = blockIdx.x * kSpmvWarps + w;
+    int r = wi < nrows ? rowlist[wi] : 0;
+    long long b0 = 0, b1 = 0;
+    if (wi < nrows) {
+      b0 = ptr[r];
+      b1 = ptr[r + 1];
+    }
+    while (wi < nrows) {
+      const int win = wi + nw;
+      const int rn = win < nrows ? rowlist[win] : 0;  // next descriptor: in flight while this row streams
+      long long nb0 = 0, nb1 = 0;
+      if (win < nrows) {
+        nb0 = ptr[rn];
+        nb1 = ptr[rn + 1];
+      }
+      const float yold = (lane == 0 && scale_ptr) ? y[r] : 0.0f;
+      double acc = 0.0;
+      for (long long b = b0 + lane; b < b1; b += 128) {
+        int p[4];
+        float4 v0[4], v1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const long long bb = b + 32 * u;
+          const bool ok = bb < b1;
+          p[u] = ok ? pos[bb] : 0;
+          v0[u] = ok ? val[2 * bb] : make_float4(0.f, 0.f, 0.f, 0.f);
+          v1[u] = ok ? val[2 * bb + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          acc += dot8(v0[u], v1[u], __ldg(x4 + 2 * (size_t)p[u]), __ldg(x4 + 2 * (size_t)p[u] + 1));
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float y0 = scale_ptr ? s * yold : 0.0f;
+        const float yn = (float)((double)y0 + acc);
+        y[r] = yn;
+        sq += (double)yn * (double)yn;
+      }
+      wi = win;
+      r = rn;
+      b0 = nb0;
+      b1 = nb1;
+    }
+  }
+  if (partial) {
+    if (lane == 0) sh[w] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int k = 0; k < kSpmvWarps; k++) t += sh[k];
+      partial[blockIdx.x] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSpmvWarps * 32, kPersistBlocksPerSM)
+k_bspmv_cols_p(const long long *__restrict__ ptr, const int *__restrict__ row, const float4 *__restrict__ val,
+               const float *__restrict__ u, float *__restrict__ y, const float *__restrict__ scale_ptr,
+               float scale_sign, const int *__restrict__ collist, int ncols, double *__restrict__ partial,
+               const int *__restrict__ stop) {
+  __shared__ double sh[kSpmvWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = gridDim.x * kSpmvWarps;
+  double sq = 0.0;
+  if (stop == nullptr || *stop == 0) {
+    const float s = scale_ptr ? scale_sign * (*scale_ptr) : 0.0f;
+    int wi = blockIdx.x * kSpmvWarps + w;
+    int c = wi < ncols ? collist[wi] : 0;
+    long long b0 = 0, b1 = 0;
+    if (wi < ncols) {
+      b0 = ptr[c];
+      b1 = ptr[c + 1];
+    }
+    while (wi < ncols) {
+      const int win = wi + nw;
+      const int cn = win < ncols ? collist[win] : 0;
+      long long nb0 = 0, nb1 = 0;
+      if (win < ncols) {
+        nb0 = ptr[cn];
+        nb1 = ptr[cn + 1];
+      }
+      float4 yo0 = make_float4(0.f, 0.f, 0.f, 0.f), yo1 = yo0;
+      if (lane == 0 && scale_ptr) {
+        yo0 = reinterpret_cast<const float4 *>(y)[2 * (size_t)c];
+        yo1 = reinterpret_cast<const float4 *>(y)[2 * (size_t)c + 1];
+      }
+      double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (long long b = b0 + lane; b < b1; b += 128) {
+        int rr[4];
+        float4 v0[4], v1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const long long bb = b + 32 * q;
+          const bool ok = bb < b1;
+          rr[q] = ok ? row[bb] : 0;
+          v0[q] = ok ? val[2 * bb] : make_float4(0.f, 0.f, 0.f, 0.f);
+          v1[q] = ok ? val[2 * bb + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double uu = (double)__ldg(u + rr[q]);
+          a[0] += (double)v0[q].x * uu; a[1] += (double)v0[q].y * uu; a[2] += (double)v0[q].z * uu; a[3] += (double)v0[q].w * uu;
+          a[4] += (double)v1[q].x * uu; a[5] += (double)v1[q].y * uu; a[6] += (double)v1[q].z * uu; a[7] += (double)v1[q].w * uu;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = warp_sum(a[k]);
+      if (lane == 0) {
+        const float yo[8] = {yo0.x, yo0.y, yo0.z, yo0.w, yo1.x, yo1.y, yo1.z, yo1.w};
+        float yn[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const float y0 = scale_ptr ? s * yo[k] : 0.0f;
+          yn[k] = (float)((double)y0 + a[k]);
+          sq += (double)yn[k] * (double)yn[k];
+        }
+        reinterpret_cast<float4 *>(y)[2 * (size_t)c] = make_float4(yn[0], yn[1], yn[2], yn[3]);
+        reinterpret_cast<float4 *>(y)[2 * (size_t)c + 1] = make_float4(yn[4], yn[5], yn[6], yn[7]);
+      }
+      wi = win;
+      c = cn;
+      b0 = nb0;
+      b1 = nb1;
+    }
+  }
+  if (partial) {
+    if (lane == 0) sh[w] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int k = 0; k < kSpmvWarps; k++) t += sh[k];
+      partial[blockIdx.x] = t;
+    }
   }
 }
 
@@ -1049,7 +1211,13 @@ struct Compressed {
   int nrows = 0, nlong = 0, nshort = 0;
   int kind = 0;  // 0 scalar CSR/CSC, 1 depth-blocked rows, 2 depth-blocked vertex columns
   long long nblk = 0;
-  int blocks() const { return (nlong + kSpmvWarps - 1) / kSpmvWarps + (nshort + 255) / 256; }
+  // grid of the long-row kernel: one warp per row (generic layout) or the persistent grid (blocked layouts)
+  int long_grid() const {
+    const int per_row = (nlong + kSpmvWarps - 1) / kSpmvWarps;
+    if (kind == 0 || getenv("DSURF_LSMR_NO_PERSIST") != nullptr) return per_row;
+    return std::min(per_row, sm_count() * kPersistBlocksPerSM);
+  }
+  int blocks() const { return long_grid() + (nshort + 255) / 256; }
 };
 
 struct dsurf_lsmr_sys {
@@ -1114,6 +1282,8 @@ static int classify_rows(cudaStream_t st, Compressed &C, int nrows) {
     else
       sh.push_back(r);  // includes empty rows (they still need y = s*y)
   }
+  // longest first: the persistent kernels stride over this list, so every warp gets the same mix of lengths
+  std::stable_sort(lo.begin(), lo.end(), [&](int a, int b) { return hp[a + 1] - hp[a] > hp[b + 1] - hp[b]; });
   C.nrows = nrows;
   C.nlong = (int)lo.size();
   C.nshort = (int)sh.size();
@@ -1184,7 +1354,8 @@ static int build_blocked(cudaStream_t st, const int *rows1, const int *cols1, co
 // `fork` (may be null): system whose side stream runs the short-row kernel beside the long-row one
 static void launch_product(cudaStream_t st, const Compressed &C, const float *x, float *y, const float *scale_ptr,
                            float sign, double *partial, const int *stop, dsurf_lsmr_sys *fork = nullptr) {
-  const int ga = (C.nlong + kSpmvWarps - 1) / kSpmvWarps;
+  const int ga = C.long_grid();
+  const bool persist = ga != (C.nlong + kSpmvWarps - 1) / kSpmvWarps || (C.kind != 0 && getenv("DSURF_LSMR_NO_PERSIST") == nullptr);
   cudaStream_t ss = (fork && C.nlong > 0 && C.nshort > 0) ? fork_side(fork, st) : st;
   struct Join {
     dsurf_lsmr_sys *f;
@@ -1198,14 +1369,20 @@ static void launch_product(cudaStream_t st, const Compressed &C, const float *x,
     const int gb = (C.nshort + 255) / 256;
     if (C.kind == 1) {
       const float4 *x4 = reinterpret_cast<const float4 *>(x);
-      if (C.nlong > 0)
+      if (C.nlong > 0 && persist)
+        k_bspmv_rows_p<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.longl.p, C.nlong,
+                                                       partial, stop);
+      else if (C.nlong > 0)
         k_bspmv_rows<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
                                                      partial, stop);
       if (C.nshort > 0)
         k_bspmv_rows<<<gb, 256, 0, ss>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.shortl.p, C.nshort, 1,
                                          partial ? partial + ga : nullptr, stop);
     } else {
-      if (C.nlong > 0)
+      if (C.nlong > 0 && persist)
+        k_bspmv_cols_p<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.longl.p, C.nlong,
+                                                       partial, stop);
+      else if (C.nlong > 0)
         k_bspmv_cols<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
                                                      partial, stop);
       if (C.nshort > 0)
