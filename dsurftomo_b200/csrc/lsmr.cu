@@ -292,6 +292,21 @@ k_bspmv_cols(const long long *__restrict__ ptr, const int *__restrict__ row, con
 // ---------------------------------------------------------------------------------------------
 constexpr int kPersistBlocksPerSM = 4;
 
+// one 32-byte block (8 floats) per lane in ONE request: sm_100a's 256-bit read-only load
+// (SASS LDG.E.ENL2.256.CONSTANT).  With two 128-bit loads the scattered x gather alone costs 64 L1
+// wavefronts per 32 blocks and caps the kernel near 4 TB/s; one 256-bit load halves that.
+struct __align__(32) Float8 {
+  float4 lo, hi;
+};
+__device__ __forceinline__ Float8 ldg256(const void *p) {
+  Float8 r;
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+      : "l"(p));
+  return r;
+}
+
+template <bool W256>
 __global__ void __launch_bounds__(kSpmvWarps * 32, kPersistBlocksPerSM)
 k_bspmv_rows_p(const long long *__restrict__ ptr, const int *__restrict__ pos, const float4 *__restrict__ val,
                const float4 *__restrict__ x4, float *__restrict__ y, const float *__restrict__ scale_ptr,
@@ -322,18 +337,33 @@ k_bspmv_rows_p(const long long *__restrict__ ptr, const int *__restrict__ pos, c
       double acc = 0.0;
       for (long long b = b0 + lane; b < b1; b += 128) {
         int p[4];
-        float4 v0[4], v1[4];
+        Float8 v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const long long bb = b + 32 * u;
           const bool ok = bb < b1;
           p[u] = ok ? pos[bb] : 0;
-          v0[u] = ok ? val[2 * bb] : make_float4(0.f, 0.f, 0.f, 0.f);
-          v1[u] = ok ? val[2 * bb + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u].lo = v[u].hi = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            if (W256) {
+              v[u] = ldg256(val + 2 * bb);
+            } else {
+              v[u].lo = val[2 * bb];
+              v[u].hi = val[2 * bb + 1];
+            }
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-          acc += dot8(v0[u], v1[u], __ldg(x4 + 2 * (size_t)p[u]), __ldg(x4 + 2 * (size_t)p[u] + 1));
+        for (int u = 0; u < 4; u++) {
+          Float8 xx;
+          if (W256) {
+            xx = ldg256(x4 + 2 * (size_t)p[u]);
+          } else {
+            xx.lo = __ldg(x4 + 2 * (size_t)p[u]);
+            xx.hi = __ldg(x4 + 2 * (size_t)p[u] + 1);
+          }
+          acc += dot8(v[u].lo, v[u].hi, xx.lo, xx.hi);
+        }
       }
       acc = warp_sum(acc);
       if (lane == 0) {
@@ -359,6 +389,7 @@ k_bspmv_rows_p(const long long *__restrict__ ptr, const int *__restrict__ pos, c
   }
 }
 
+template <bool W256>
 __global__ void __launch_bounds__(kSpmvWarps * 32, kPersistBlocksPerSM)
 k_bspmv_cols_p(const long long *__restrict__ ptr, const int *__restrict__ row, const float4 *__restrict__ val,
                const float *__restrict__ u, float *__restrict__ y, const float *__restrict__ scale_ptr,
@@ -393,20 +424,28 @@ k_bspmv_cols_p(const long long *__restrict__ ptr, const int *__restrict__ row, c
       double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (long long b = b0 + lane; b < b1; b += 128) {
         int rr[4];
-        float4 v0[4], v1[4];
+        Float8 vv[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const long long bb = b + 32 * q;
           const bool ok = bb < b1;
           rr[q] = ok ? row[bb] : 0;
-          v0[q] = ok ? val[2 * bb] : make_float4(0.f, 0.f, 0.f, 0.f);
-          v1[q] = ok ? val[2 * bb + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+          vv[q].lo = vv[q].hi = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            if (W256) {
+              vv[q] = ldg256(val + 2 * bb);
+            } else {
+              vv[q].lo = val[2 * bb];
+              vv[q].hi = val[2 * bb + 1];
+            }
+          }
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const double uu = (double)__ldg(u + rr[q]);
-          a[0] += (double)v0[q].x * uu; a[1] += (double)v0[q].y * uu; a[2] += (double)v0[q].z * uu; a[3] += (double)v0[q].w * uu;
-          a[4] += (double)v1[q].x * uu; a[5] += (double)v1[q].y * uu; a[6] += (double)v1[q].z * uu; a[7] += (double)v1[q].w * uu;
+          const float4 v0 = vv[q].lo, v1 = vv[q].hi;
+          a[0] += (double)v0.x * uu; a[1] += (double)v0.y * uu; a[2] += (double)v0.z * uu; a[3] += (double)v0.w * uu;
+          a[4] += (double)v1.x * uu; a[5] += (double)v1.y * uu; a[6] += (double)v1.z * uu; a[7] += (double)v1.w * uu;
         }
       }
 #pragma unroll
@@ -1212,10 +1251,18 @@ struct Compressed {
   int kind = 0;  // 0 scalar CSR/CSC, 1 depth-blocked rows, 2 depth-blocked vertex columns
   long long nblk = 0;
   // grid of the long-row kernel: one warp per row (generic layout) or the persistent grid (blocked layouts)
+  // Blocked rows (kind 1): persistent grid, kPersistBlocksPerSM CTAs per SM.  Blocked vertex columns
+  // (kind 2): one warp per column, longest first -- columns are ~4x longer than rows and few (P), so the
+  // hardware block scheduler balances them better than a fixed stride (measured: 116 vs 159 us).
+  // DSURF_LSMR_GRID_ROWS / DSURF_LSMR_GRID_COLS = CTAs per SM (0 = one warp per row) override for A/B runs.
   int long_grid() const {
     const int per_row = (nlong + kSpmvWarps - 1) / kSpmvWarps;
-    if (kind == 0 || getenv("DSURF_LSMR_NO_PERSIST") != nullptr) return per_row;
-    return std::min(per_row, sm_count() * kPersistBlocksPerSM);
+    if (kind == 0) return per_row;
+    int per_sm = kind == 1 ? kPersistBlocksPerSM : 0;
+    if (const char *e = getenv(kind == 1 ? "DSURF_LSMR_GRID_ROWS" : "DSURF_LSMR_GRID_COLS")) per_sm = atoi(e);
+    if (kind == 1 ? getenv("DSURF_LSMR_OLD_ROWS") != nullptr : getenv("DSURF_LSMR_NEW_COLS") == nullptr) per_sm = 0;
+    if (per_sm <= 0) return per_row;
+    return std::min(per_row, sm_count() * per_sm);
   }
   int blocks() const { return long_grid() + (nshort + 255) / 256; }
 };
@@ -1355,7 +1402,14 @@ static int build_blocked(cudaStream_t st, const int *rows1, const int *cols1, co
 static void launch_product(cudaStream_t st, const Compressed &C, const float *x, float *y, const float *scale_ptr,
                            float sign, double *partial, const int *stop, dsurf_lsmr_sys *fork = nullptr) {
   const int ga = C.long_grid();
-  const bool persist = ga != (C.nlong + kSpmvWarps - 1) / kSpmvWarps || (C.kind != 0 && getenv("DSURF_LSMR_NO_PERSIST") == nullptr);
+  // Measured on B200 (gpurun_out/s13_*.json, probe system of cfg-3 shape, us per product):
+  //   rows: first-generation warp-per-row 118.5 | persistent + 4 blocks in flight, 128-bit loads 116.2 | 256-bit 112.2
+  //   cols: first-generation warp-per-column (longest first) 115.5 | 4 blocks in flight, 128-bit 126.3 | 256-bit 167.3
+  // so rows use k_bspmv_rows_p<256-bit> and columns keep k_bspmv_cols.  A/B knobs: DSURF_LSMR_OLD_ROWS=1,
+  // DSURF_LSMR_NEW_COLS=1, DSURF_LSMR_W128=1.
+  static const bool old_rows = getenv("DSURF_LSMR_OLD_ROWS") != nullptr, old_cols = getenv("DSURF_LSMR_NEW_COLS") == nullptr;
+  static const bool w256 = getenv("DSURF_LSMR_W128") == nullptr;
+  const bool persist = (C.kind == 1 && !old_rows) || (C.kind == 2 && !old_cols);
   cudaStream_t ss = (fork && C.nlong > 0 && C.nshort > 0) ? fork_side(fork, st) : st;
   struct Join {
     dsurf_lsmr_sys *f;
@@ -1370,8 +1424,8 @@ static void launch_product(cudaStream_t st, const Compressed &C, const float *x,
     if (C.kind == 1) {
       const float4 *x4 = reinterpret_cast<const float4 *>(x);
       if (C.nlong > 0 && persist)
-        k_bspmv_rows_p<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.longl.p, C.nlong,
-                                                       partial, stop);
+        (w256 ? k_bspmv_rows_p<true> : k_bspmv_rows_p<false>)<<<ga, kSpmvWarps * 32, 0, st>>>(
+            C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.longl.p, C.nlong, partial, stop);
       else if (C.nlong > 0)
         k_bspmv_rows<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x4, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
                                                      partial, stop);
@@ -1380,8 +1434,8 @@ static void launch_product(cudaStream_t st, const Compressed &C, const float *x,
                                          partial ? partial + ga : nullptr, stop);
     } else {
       if (C.nlong > 0 && persist)
-        k_bspmv_cols_p<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.longl.p, C.nlong,
-                                                       partial, stop);
+        (w256 ? k_bspmv_cols_p<true> : k_bspmv_cols_p<false>)<<<ga, kSpmvWarps * 32, 0, st>>>(
+            C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.longl.p, C.nlong, partial, stop);
       else if (C.nlong > 0)
         k_bspmv_cols<<<ga, kSpmvWarps * 32, 0, st>>>(C.ptr.p, C.idx.p, v4, x, y, scale_ptr, sign, C.longl.p, C.nlong, 0,
                                                      partial, stop);
