@@ -107,6 +107,13 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def measured_traffic():
+    """DRAM bytes measured with ncu (profiles/r01_traffic.json): per sweep of the eikonal kernel at cfg 3 and
+    per non-zero per LSMR iteration.  Scaled by the units of one launch in the roofline objects."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
 def lsmr_bytes(nnz, m, n):
     return 16 * nnz + 8 * (m + 1) + 12 * m + 80 * n  # SURVEY.md section 8(d)
 
@@ -208,7 +215,7 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
 
     # ---------------- timed region 1: device-resident sweep stage (CUDA events on the launching stream)
     sampler = ClockSampler(local)
-    dev_ms, eik_ms, nsw_local, launches, wall = 0.0, 0.0, 0, 0, 0.0
+    dev_ms, eik_ms, nsw_local, launches, wall, launches_eik = 0.0, 0.0, 0, 0, 0.0, 0
     stage = dict(eikonal_ms=0.0, rays_ms=0.0, assembly_ms=0.0)
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
@@ -225,6 +232,7 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
             eik_ms += tm["eikonal_ms"]
             nsw_local += tm["sweeps"]
             launches += tm["launches"]
+            launches_eik += tm["eikonal_launches"]
             for k in stage:
                 stage[k] += tm[k]
     barrier()
@@ -237,10 +245,17 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
     b_sweep = 8 * (Nc + 129 * 129)  # veln read + ttn write, coarse + refined
     peak, peak_src = peaks()
     achieved = b_sweep * nsw_local / (eik_ms / 1e3) / 1e9
-    roofline = dict(bound="hbm", kernel="k_eikonal (+ node-state fill)", achieved=achieved, peak=peak, unit="GB/s",
-                    frac=achieved / peak, traffic=None, peak_source=peak_src,
-                    algorithmic_bytes_per_sweep=b_sweep, launches=int(args.steps),
-                    note="latency/dependency-bound exact-order FMM replay; see DESIGN.md")
+    n_eik_launches = max(1, int(round(launches_eik)))
+    mt = measured_traffic()
+    traffic = None
+    if mt and pb.nx == 131:  # measured at cfg 3 only
+        traffic = mt["eikonal"]["dram_bytes_per_sweep"] * nsw_local / n_eik_launches
+    roofline = dict(bound="hbm", kernel="k_eikonal3<16> (+ node-state fill)", achieved=achieved, peak=peak, unit="GB/s",
+                    frac=achieved / peak, traffic=traffic, peak_source=peak_src,
+                    algorithmic_bytes_per_sweep=b_sweep, algorithmic_bytes_per_launch=b_sweep * nsw_local / n_eik_launches,
+                    launches=n_eik_launches, avg_launch_ms=eik_ms / n_eik_launches,
+                    traffic_source=(mt["eikonal"]["source"] if traffic else None),
+                    note="issue-bound exact-order FMM replay; DRAM traffic ~250x the algorithmic bytes; see DESIGN.md section 4")
 
     # ---------------- timed region 2: end to end through the host-buffer API (H2D + compute + D2H)
     last = plan.download()  # sizes the pinned output buffers from the last timed step
@@ -331,9 +346,13 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
             host = None
         lsmr = dict(iters_per_s=it_s, iters=L["itn"], nnz=int(nnz_tot), m=int(m_tot), n=n, build_s=t_build,
                     roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
-                                  spmv_gbs=ach_spmv, spmtv_gbs=ach_spmtv, traffic=None,
-                                  algorithmic_bytes_per_iter=lsmr_bytes(sysl.nnz, m, n)),
-                    launches_per_iter=28, host_buffer_call=host)
+                                  spmv_gbs=ach_spmv, spmtv_gbs=ach_spmtv,
+                                  traffic=(mt["lsmr"]["dram_bytes_per_nnz_per_iter"] * sysl.nnz if mt else None),
+                                  traffic_source=(mt["lsmr"]["source"] if mt else None),
+                                  algorithmic_bytes_per_iter=lsmr_bytes(sysl.nnz, m, n),
+                                  note="depth-blocked layout stores 1 index + 8 values per vertex: real bytes are "
+                                       "~0.58x the algorithmic 16 B per non-zero"),
+                    launches_per_iter=(6 if world == 1 else 9), host_buffer_call=host)
         sysl.close()
         if comm:
             comm.close()
