@@ -143,7 +143,7 @@ def run_reference(args, pb, pv4, sen12, blocks):
 
     O.lib()
     cores = os.cpu_count() or 1
-    per_block = 64  # gathers of every data type per step: ~10 s of work on 16-128 host threads
+    per_block = 128  # gathers of every data type per step: ~10 s of work on 16 host threads, less on more
     nsw_tot, t_tot = 0, 0.0
     for s in range(args.warmup + args.steps):
         nsw, t = cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, s, cores)
@@ -379,7 +379,7 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         import oracle_lib as O
 
         cores = os.cpu_count() or 1
-        per_block = 64  # ~10 s of CPU work on 16-128 host threads
+        per_block = 128  # ~10 s of CPU work on 16 host threads (fewer seconds on more cores)
         nsw, t = cpu_sweep_sample(pb, pv4, sen12, tblocks, per_block, 0, cores)
         cpu = dict(value=nsw / t, unit="sweeps/s", cores=cores, kind="port",
                    sample=f"{per_block} gathers of each of {len(tblocks)} data types ({nsw} sweeps, {t:.1f} s), "

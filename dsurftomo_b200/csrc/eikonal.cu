@@ -999,9 +999,12 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
     }
     // heap slot of this lane's own neighbour if the pop moves it (node ids are never -1)
     int xmown = -1;
+    // LAZY: compare every moved entry with this lane's neighbour.  Eager (exact slots in xn.y): the entries a
+    // sift-down moves are exactly the ancestors-or-self of the slot where the last element lands, each going to
+    // its parent -- decided once after the sift-down (see below) instead of once per level.
 #define TRACK_MOVE(nid, newpos) \
   {                             \
-    if ((nid) == oidx) xmown = (newpos); \
+    if (LAZY && (nid) == oidx) xmown = (newpos); \
   }
     // ---- (2) downtree (:816-885)
     if (ntr == 1) {
@@ -1014,7 +1017,8 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
       int tpp = 1, tpc = 2;
       bool stop = false;
       while (!stop && tpc < ntr && tpc + 1 < kHS3) {
-        const int2 e1 = H.sm[tpc], e2 = H.sm[tpc + 1];
+        const int4 e12 = *reinterpret_cast<const int4 *>(H.sm + tpc);  // both children in one 16-byte load (tpc is even)
+        const int2 e1 = make_int2(e12.x, e12.y), e2 = make_int2(e12.z, e12.w);
         int2 ec = e1;
         if (keyf(e1) > keyf(e2)) {
           tpc = tpc + 1;
@@ -1090,6 +1094,15 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
       H.set(tpp, m);
       if (!LAZY || tpp >= kHS3 || ntr + 1 >= kHS3) G.node[m.y].y = tpp;  // ntr + 1 = slot m came from
       TRACK_MOVE(m.y, tpp);
+      if (!LAZY) {
+        const int p = xn.y;  // slot of this lane's neighbour before the pop (exact; <= 0: not in the heap)
+        if (p == ntr + 1) {
+          xmown = tpp;       // it was the last element
+        } else if (p >= 2) {
+          const int d = __clz(p) - __clz(tpp);  // depth(tpp) - depth(p)
+          if (d >= 0 && (tpp >> d) == p) xmown = p >> 1;
+        }
+      }
       lastOK = false;
     }
 #undef TRACK_MOVE
