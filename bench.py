@@ -162,7 +162,7 @@ def run_reference(args, pb, pv4, sen12, blocks):
                cpu_baseline=dict(value=value, unit="sweeps/s", cores=cores, kind="port", sample=sample),
                e2e=dict(value=value, unit="sweeps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out))
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -411,13 +411,31 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
                    gpu_launches=int(launches), clocks=clocks,
                    stage_ms_per_step={k: v / args.steps for k, v in stage.items()}, wall_s_timed=wall,
                    lsmr=lsmr, dispersion=disp, impl="b200")
-        print(json.dumps(out))
+        emit(out)
     plan.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, library
+    chatter) was redirected to stderr in main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)  # C-level writers to fd 1 (e.g. "NCCL version ...") now land on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
