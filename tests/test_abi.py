@@ -60,3 +60,23 @@ def test_synthetic_generator_shapes():
     # periods are 1-based indices inside each type; blocks are ordered Rc, Rg, Lc, Lg
     assert np.array_equal(pb.wavetype[:, 0], [2] * 6 + [1] * 6)
     assert np.array_equal(pb.igrt[:, 0], [0] * 3 + [1] * 3 + [0] * 3 + [1] * 3)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (the CPU restatement; runs without a GPU): exactly one JSON line on stdout with
+    the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "0",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
