@@ -137,3 +137,47 @@ def test_driver_two_outer_iterations_match_oracle_chain(taipei, tmp_path):
     log = open(tmp_path / "DSurfTomo.in.log").read()
     assert log.count("Maximum and Average DWS values:") == 2 and log.count("th iteration...") == 2
     assert "min and max velocity variation" in log and "Program finishes successfully" in log
+
+
+@pytest.mark.gpu
+def test_driver_checkerboard_run(taipei, tmp_path):
+    """ifsyn = 1 (main.f90:323-343, 553-573): MOD.true is read, `synthetic` replaces the observed times by forward
+    times through it (noiselevel 0 -> deterministic), one outer iteration runs on them, and Vs_model.real /
+    <input>Syn.dat are written.  Checked against the oracle's `synthetic` and the files' contents."""
+    import shutil
+
+    _need_bin()
+    pb = taipei
+    src = os.path.dirname(TAIPEI_IN)
+    for f in ("surfdataTB.dat", "MOD"):
+        shutil.copy(os.path.join(src, f), tmp_path / f)
+    lines = open(TAIPEI_IN).read().splitlines()
+    lines[18] = "1                                c: synthetic flag(0:real data,1:synthetic)"
+    lines[19] = "0.0                              c: noiselevel"
+    (tmp_path / "DSurfTomo.in").write_text("\n".join(lines) + "\n")
+    ii = np.arange(pb.nx)[None, None, :]
+    jj = np.arange(pb.ny)[None, :, None]
+    vtrue = np.clip(pb.vsf + 0.1 * np.sin(0.7 * ii) * np.sin(0.7 * jj), pb.minvel, pb.maxvel).astype(np.float32)
+    with open(tmp_path / "MOD.true", "w") as fh:  # no depth line (main.f90:330-336)
+        for k in range(pb.nz):
+            for j in range(pb.ny):
+                fh.write(" ".join("%.5f" % v for v in vtrue[k, j]) + "\n")
+    vtrue = np.array([[["%.5f" % v for v in row] for row in pl] for pl in vtrue], dtype=np.float64).astype(np.float32)
+    r = subprocess.run([BIN, str(tmp_path / "DSurfTomo.in"), "--maxiter", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "Synthetic Test Begin" in r.stdout and "Vs_model.real" in r.stdout
+    ref = O.synthetic(pb, vels=vtrue, nthreads=8)
+    assert ref["err"] == 0
+    res = np.loadtxt(tmp_path / "residualFirst.dat")
+    assert np.abs(res[:, 2] / ref["obst"] - 1).max() <= 1e-5          # obst column = synthetic forward times
+    real = _read_model_file(tmp_path / "Vs_model.real", pb)
+    want = vtrue[: pb.nz - 1, 1:-1, 1:-1].ravel()
+    assert np.abs(real[:, 3] - want).max() <= 5.1e-6
+    syn = _read_model_file(tmp_path / "DSurfTomo.inSyn.dat", pb)
+    it1 = _read_model_file(tmp_path / "DSurfTomo.inMeasure.dat.iter001", pb)
+    assert np.array_equal(syn, it1) and not os.path.exists(tmp_path / "DSurfTomo.inMeasure.dat")
+    for name in ("velmap2dRc.dat",):
+        assert os.path.exists(tmp_path / name)
+    # the inversion moved the start model towards the checkerboard
+    start = pb.vsf[: pb.nz - 1, 1:-1, 1:-1].ravel()
+    assert np.abs(syn[:, 3] - want).mean() < np.abs(start - want).mean()
