@@ -215,7 +215,7 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
 
     # ---------------- timed region 1: device-resident sweep stage (CUDA events on the launching stream)
     sampler = ClockSampler(local)
-    dev_ms, eik_ms, nsw_local, launches, wall, launches_eik = 0.0, 0.0, 0, 0, 0.0, 0
+    dev_ms, eik_ms, nsw_local, launches, wall, launches_eik, nrays_local = 0.0, 0.0, 0, 0, 0.0, 0, 0
     stage = dict(eikonal_ms=0.0, rays_ms=0.0, assembly_ms=0.0)
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
@@ -227,6 +227,8 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         plan.reset_rows()
         plan.sweeps(g0, g1)
         if s >= args.warmup:
+            r0_, r1_ = ddist.rows_of_gathers(pb, g0, g1)
+            nrays_local += r1_ - r0_
             tm = plan.timings()
             dev_ms += tm["total_ms"]
             eik_ms += tm["eikonal_ms"]
@@ -410,6 +412,10 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
                                                  "with host buffers (pinned outputs)"),
                    gpu_launches=int(launches), clocks=clocks,
                    stage_ms_per_step={k: v / args.steps for k, v in stage.items()}, wall_s_timed=wall,
+                   rays=dict(rays_per_s=(nrays_local / (stage["rays_ms"] / 1e3) if stage["rays_ms"] > 0 else None),
+                             rows_per_s=(nrays_local / (stage["assembly_ms"] / 1e3) if stage["assembly_ms"] > 0 else None),
+                             note="rank 0: receiver times + ray back-trace (k_rays) and Frechet row assembly, rays per second "
+                                  "of their own stage time (SURVEY.md 8d: latency-bound gathers, no HBM fraction quoted)"),
                    lsmr=lsmr, dispersion=disp, impl="b200")
         emit(out)
     plan.close()

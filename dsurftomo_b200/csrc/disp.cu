@@ -89,19 +89,81 @@ void make_layer_tables(const float *depz, int nz, float minthk0, LayerTables &T)
 // device: period equations
 // ------------------------------------------------------------------------------------------
 struct Stack {            // view of one thread's layer stack in shared memory
-  const float *a, *b, *rho;  // element m (1-based layer) at [(m-1)*stride]
+  float *a, *b, *rho;        // element m (1-based layer) at [(m-1)*stride]
   const float *d;            // shared flattened thicknesses, [m-1]
   int stride, mmax, llw;
+  __device__ __forceinline__ float af(int m) const { return a[(m - 1) * stride]; }
+  __device__ __forceinline__ float bf(int m) const { return b[(m - 1) * stride]; }
   __device__ __forceinline__ double A(int m) const { return (double)a[(m - 1) * stride]; }
   __device__ __forceinline__ double B(int m) const { return (double)b[(m - 1) * stride]; }
   __device__ __forceinline__ double R(int m) const { return (double)rho[(m - 1) * stride]; }
   __device__ __forceinline__ double D(int m) const { return (double)d[m - 1]; }
+  // sphere(ifunc, 1): rho = rtp * btp**(-5 | -2.275)
+  __device__ __forceinline__ void apply_fac(const float *fac) {
+    if (fac)
+      for (int i = 1; i <= mmax; i++) rho[(i - 1) * stride] = rho[(i - 1) * stride] * fac[i - 1];
+  }
+};
+
+// On-the-fly stack of one finite-difference VARIANT of a column (depthkernel, CalSurfG.f90:76-160).
+// A variant differs from its column's base model in ONE parameter of ONE depth node, i.e. in the few
+// refined layers interpolated from that node.  The base stack is stored once per column in shared
+// memory (396 B per column instead of per thread: the per-thread stacks were what limited the kernel to
+// 16 warps per SM); a perturbed layer is recomputed from the node values with the statements of
+// refineGrid2LayerMdl + sphere, in the same order, so every value is bit-identical to the stored form.
+struct StackOTF {
+  const float *a, *b, *rho;      // base stack of this thread's column, contiguous [m-1]; rho already * fac
+  const float *d;
+  const float *nval;             // node values of the perturbed parameter of this column, [nz] (base)
+  const int *lnode;              // refined layer -> upper node
+  const float *wnum, *wden, *fac;
+  const double *tmpfac;
+  int pnode, pwhich, psign;      // perturbed node (-1 none), parameter (0 vs, 1 vp, 2 rho), sign (0: -, 1: +)
+  int nz, mmax, llw;
+  __device__ __forceinline__ bool hit(int k) const {
+    if (pnode < 0) return false;
+    if (k == mmax - 1) return pnode == nz - 1;
+    const int i = lnode[k];
+    return i == pnode || i + 1 == pnode;
+  }
+  __device__ __forceinline__ float node(int i) const {  // node value with the +-0.5 % perturbation
+    const float v = nval[i];
+    if (i != pnode) return v;
+    const float hf = 0.5f * 0.01f;
+    return psign ? v + hf * v : v - hf * v;
+  }
+  __device__ __forceinline__ float layer(int k) const {  // refineGrid2LayerMdl interpolation
+    if (k == mmax - 1) return node(nz - 1);
+    const int i = lnode[k];
+    const float lo = node(i), hi = node(i + 1);
+    return lo + wnum[k] * (hi - lo) / wden[k];
+  }
+  __device__ __forceinline__ float bf(int m) const {
+    const int k = m - 1;
+    if (pwhich != 0 || !hit(k)) return b[k];
+    return (float)((double)layer(k) * tmpfac[k]);
+  }
+  __device__ __forceinline__ float af(int m) const {
+    const int k = m - 1;
+    if (pwhich != 1 || !hit(k)) return a[k];
+    return (float)((double)layer(k) * tmpfac[k]);
+  }
+  __device__ __forceinline__ double A(int m) const { return (double)af(m); }
+  __device__ __forceinline__ double B(int m) const { return (double)bf(m); }
+  __device__ __forceinline__ double R(int m) const {
+    const int k = m - 1;
+    if (pwhich != 2 || !hit(k)) return (double)rho[k];
+    return (double)(layer(k) * fac[k]);
+  }
+  __device__ __forceinline__ double D(int m) const { return (double)d[m - 1]; }
+  __device__ __forceinline__ void apply_fac(const float *) {}  // folded into the base stack / R()
 };
 
 __device__ __forceinline__ double dsign1(double x) { return copysign(1.0, x); }
 
 // surfdisp96.f:704-761
-__device__ double dltar1(double wvno, double omega, const Stack &L) {
+template <class STK>
+__device__ double dltar1(double wvno, double omega, const STK &L) {
   const int mmax = L.mmax;
   double beta1 = L.B(mmax);
   double rho1 = L.R(mmax);
@@ -212,7 +274,8 @@ __device__ __forceinline__ void var_psv(double p, double q, double ra, double rb
 
 // surfdisp96.f:767-864 with dnka (:1018-1062) and normc (:989-1014) inlined; the 5x5 Dunkin
 // matrix is formed column by column so only one column is live at a time.
-__device__ double dltar4(double wvno, double omga, const Stack &L) {
+template <class STK>
+__device__ double dltar4(double wvno, double omga, const STK &L) {
   const int mmax = L.mmax;
   double omega = omga;
   if (omega < 1.0e-4) omega = 1.0e-4;
@@ -324,13 +387,15 @@ __device__ double dltar4(double wvno, double omga, const Stack &L) {
   return e1;
 }
 
-__device__ __forceinline__ double dltar(double wvno, double omega, int kk, const Stack &L) {
+template <class STK>
+__device__ __forceinline__ double dltar(double wvno, double omega, int kk, const STK &L) {
   return kk == 1 ? dltar1(wvno, omega, L) : dltar4(wvno, omega, L);
 }
 
 // surfdisp96.f:551-668 (half inlined, :670-680)
+template <class STK>
 __device__ double nevill(double t, double c1, double c2, double del1, double del2, int ifunc,
-                         const Stack &L, double twopi) {
+                         const STK &L, double twopi) {
   double x[12], y[12];
   double c3, del3;
   int m = 1;
@@ -406,8 +471,9 @@ __device__ double nevill(double t, double c1, double c2, double del1, double del
 }
 
 // surfdisp96.f:384-476
+template <class STK>
 __device__ void getsol(double t1, double &c1, double clow, double dc, double cm, float betmx,
-                       int &iret, int ifunc, int ifirst, const Stack &L, double &del1st) {
+                       int &iret, int ifunc, int ifirst, const STK &L, double &del1st) {
   const double twopi = 2.0 * 3.141592653589793;
   double omega = twopi / t1;
   double wvno = omega / c1;
@@ -481,22 +547,16 @@ __device__ float gtsolh(float a, float b) {
 // memory (a, b hold the transformed velocities, rtp the untransformed density).
 // smem arrays: sa, sb, srho (work), with rho rewritten per wave type from rtp * fac.
 // c_prev[] (kmax doubles, thread-private global scratch) holds c(k) for higher modes.
-__device__ void surfdisp_core(float *sa, float *sb, float *srho, const float *d, const float *fac,
-                              int stride, int mmax, int ifunc, int mode, int igr, int kmax,
-                              const double *t, double *cg, double *cwork) {
-  Stack L;
-  L.a = sa;
-  L.b = sb;
-  L.rho = srho;
-  L.d = d;
-  L.stride = stride;
-  L.mmax = mmax;
+template <class STK>
+__device__ void surfdisp_core_t(STK &L, const float *fac, int ifunc, int mode, int igr, int kmax, const double *t,
+                                double *cg, double *cwork) {
+  const int mmax = L.mmax;
   L.llw = 1;
-  if (sb[0] <= 0.0f) L.llw = 2;
+  if (L.bf(1) <= 0.0f) L.llw = 2;
   int jmn = 1, jsol = 1;
   float betmx = -1.e20f, betmn = 1.e20f;
   for (int i = 1; i <= mmax; i++) {
-    const float bi = sb[(i - 1) * stride], ai = sa[(i - 1) * stride];
+    const float bi = L.bf(i), ai = L.af(i);
     if (bi > 0.01f && bi < betmn) {
       betmn = bi;
       jmn = i;
@@ -508,9 +568,7 @@ __device__ void surfdisp_core(float *sa, float *sb, float *srho, const float *d,
     }
     if (bi > betmx) betmx = bi;
   }
-  // sphere(ifunc, 1): rho = rtp * btp**(-5 | -2.275)
-  if (fac)
-    for (int i = 1; i <= mmax; i++) srho[(i - 1) * stride] = srho[(i - 1) * stride] * fac[i - 1];
+  L.apply_fac(fac);
   const float ddc = 0.005f, sone = 1.500f, h = 0.005f;
   const double one = 1.0e-2;
   const double onea = (double)sone;
@@ -518,7 +576,7 @@ __device__ void surfdisp_core(float *sa, float *sb, float *srho, const float *d,
   if (jsol == 0)
     cc1 = betmn;
   else
-    cc1 = gtsolh(sa[(jmn - 1) * stride], sb[(jmn - 1) * stride]);
+    cc1 = gtsolh(L.af(jmn), L.bf(jmn));
   cc1 = .95f * cc1;
   cc1 = .90f * cc1;
   const double cc = (double)cc1;
@@ -602,6 +660,21 @@ __device__ void surfdisp_core(float *sa, float *sb, float *srho, const float *d,
   }
 }
 
+// per-thread shared-memory stacks (surfdisp96 drop-in, first-generation column kernel)
+__device__ void surfdisp_core(float *sa, float *sb, float *srho, const float *d, const float *fac,
+                              int stride, int mmax, int ifunc, int mode, int igr, int kmax,
+                              const double *t, double *cg, double *cwork) {
+  Stack L;
+  L.a = sa;
+  L.b = sb;
+  L.rho = srho;
+  L.d = d;
+  L.stride = stride;
+  L.mmax = mmax;
+  L.llw = 1;
+  surfdisp_core_t(L, fac, ifunc, mode, igr, kmax, t, cg, cwork);
+}
+
 // gfortran powi trees
 __device__ __forceinline__ float pow3f(float x) { return x * (x * x); }
 __device__ __forceinline__ float pow4f(float x) { const float x2 = x * x; return x2 * x2; }
@@ -611,6 +684,7 @@ __device__ __forceinline__ float pow5f(float x) { const float x2 = x * x; return
 // kernel A: column variants (depthkernel / caldespersion)
 // ------------------------------------------------------------------------------------------
 constexpr int kDispBlock = 64;
+constexpr int kDispOtfDefault = 0;  // see k_disp_columns_otf; set after the A/B measurement
 
 __global__ void __launch_bounds__(kDispBlock)
 k_disp_columns(const float *__restrict__ vel, int nx, int ny, int nz, int nvar, int col0, int ncol_batch,
@@ -679,6 +753,105 @@ k_disp_columns(const float *__restrict__ vel, int nx, int ny, int nz, int nvar, 
   }
   double *cg = cgbuf + (size_t)gid * kmax;
   surfdisp_core(sa, sb, srho, sd, sfac, stride, rmax, ifunc, /*mode*/ 1, igr, kmax, t, cg, nullptr);
+}
+
+// Second-generation column kernel: on-the-fly variant stacks (StackOTF).  Shared memory per block drops from
+// 25.6 KB (one stack per thread) to ~2.5 KB (one base stack per column), so residency is set by registers
+// alone: MINB = 8 (128 registers, 16 warps/SM like the first generation), 9, 10 (96 registers, 20 warps) or
+// 12 (80 registers, 24 warps).  ncu of the first generation at cfg-3 scale: FP64 pipe 28 % busy, every warp
+// waiting on dependent fixed-latency DP chains (profiles/r01_disp_cfg3.md) -- more resident warps is the lever.
+template <int MINB>
+__global__ void __launch_bounds__(kDispBlock, MINB)
+k_disp_columns_otf(const float *__restrict__ vel, int nx, int ny, int nz, int nvar, int col0, int ncol_batch,
+                   const float *__restrict__ dflat, const double *__restrict__ tmpfac,
+                   const float *__restrict__ fac, const int *__restrict__ lnode,
+                   const float *__restrict__ wnum, const float *__restrict__ wden, int rmax, int ifunc,
+                   int igr, int kmax, const double *__restrict__ t, double *__restrict__ cgbuf, int nslots) {
+  extern __shared__ double smem_d[];
+  double *stmp = smem_d;                               // [rmax]
+  float *sd = reinterpret_cast<float *>(stmp + rmax);  // [rmax]
+  float *sfac = sd + rmax;
+  float *swnum = sfac + rmax;
+  float *swden = swnum + rmax;
+  int *slnode = reinterpret_cast<int *>(swden + rmax);
+  float *slots = reinterpret_cast<float *>(slnode + rmax);  // per column: a[rmax] b[rmax] rho[rmax] nodes[3][nz]
+  const int slot_sz = 3 * rmax + 3 * nz;
+  for (int i = threadIdx.x; i < rmax; i += blockDim.x) {
+    stmp[i] = tmpfac[i];
+    sd[i] = dflat[i];
+    sfac[i] = fac[i];
+    swnum[i] = wnum[i];
+    swden[i] = wden[i];
+    slnode[i] = lnode[i];
+  }
+  const long long gid0 = (long long)blockIdx.x * blockDim.x;
+  const long long total = (long long)ncol_batch * nvar;
+  const int cfirst = (int)(gid0 / nvar);
+  const size_t plane = (size_t)nx * ny;
+  // node models of the block's columns (CalSurfG.f90:45-52: Brocher's vp(vs), rho(vp))
+  for (int it = threadIdx.x; it < nslots * nz; it += blockDim.x) {
+    const int sl = it / nz, i = it % nz;
+    if (cfirst + sl < ncol_batch) {
+      const float v = vel[(size_t)i * plane + col0 + cfirst + sl];
+      const float vp = 0.9409f + 2.0947f * v - 0.8206f * (v * v) + 0.2683f * pow3f(v) - 0.0251f * pow4f(v);
+      const float rho = 1.6612f * vp - 0.4721f * (vp * vp) + 0.0671f * pow3f(vp) - 0.0043f * pow4f(vp) +
+                        0.000106f * pow5f(vp);
+      float *nd = slots + (size_t)sl * slot_sz + 3 * rmax;
+      nd[i] = v;
+      nd[nz + i] = vp;
+      nd[2 * nz + i] = rho;
+    }
+  }
+  __syncthreads();
+  // base (unperturbed) refined + flattened stacks of the block's columns
+  for (int it = threadIdx.x; it < nslots * rmax; it += blockDim.x) {
+    const int sl = it / rmax, k = it % rmax;
+    if (cfirst + sl < ncol_batch) {
+      float *sb0 = slots + (size_t)sl * slot_sz;
+      const float *nd = sb0 + 3 * rmax;
+      float rvs, rvp, rrho;
+      if (k == rmax - 1) {
+        rvs = nd[nz - 1];
+        rvp = nd[nz + nz - 1];
+        rrho = nd[2 * nz + nz - 1];
+      } else {
+        const int i = slnode[k];
+        rvp = nd[nz + i] + swnum[k] * (nd[nz + i + 1] - nd[nz + i]) / swden[k];
+        rvs = nd[i] + swnum[k] * (nd[i + 1] - nd[i]) / swden[k];
+        rrho = nd[2 * nz + i] + swnum[k] * (nd[2 * nz + i + 1] - nd[2 * nz + i]) / swden[k];
+      }
+      const double tm = stmp[k];
+      sb0[k] = (float)((double)rvp * tm);
+      sb0[rmax + k] = (float)((double)rvs * tm);
+      sb0[2 * rmax + k] = rrho * sfac[k];
+    }
+  }
+  __syncthreads();
+  const long long gid = gid0 + threadIdx.x;
+  if (gid >= total) return;
+  const int colb = (int)(gid / nvar);
+  const int var = (int)(gid % nvar);
+  const float *sb0 = slots + (size_t)(colb - cfirst) * slot_sz;
+  StackOTF L;
+  L.a = sb0;
+  L.b = sb0 + rmax;
+  L.rho = sb0 + 2 * rmax;
+  L.d = sd;
+  L.lnode = slnode;
+  L.wnum = swnum;
+  L.wden = swden;
+  L.fac = sfac;
+  L.tmpfac = stmp;
+  L.nz = nz;
+  L.mmax = rmax;
+  L.llw = 1;
+  L.pnode = var == 0 ? -1 : (var - 1) / 6;           // variant decoding (CalSurfG.f90:76-160)
+  const int pkind = var == 0 ? 0 : (var - 1) % 6;    // 0/1 vs -/+, 2/3 vp -/+, 4/5 rho -/+
+  L.pwhich = pkind >> 1;
+  L.psign = pkind & 1;
+  L.nval = sb0 + 3 * rmax + (size_t)L.pwhich * nz;
+  double *cg = cgbuf + (size_t)gid * kmax;
+  surfdisp_core_t(L, nullptr, ifunc, /*mode*/ 1, igr, kmax, t, cg, nullptr);
 }
 
 // pv and the three finite-difference kernels from the variant curves (CalSurfG.f90:60,91-93,
@@ -764,9 +937,28 @@ int run_dispersion(cudaStream_t st, const float *d_vel, int nx, int ny, int nz, 
     const int nb = std::min(batch, ncol - c0);
     const long long nthreads = (long long)nb * nvar;
     const int grid = (int)((nthreads + kDispBlock - 1) / kDispBlock);
-    k_disp_columns<<<grid, kDispBlock, smem, st>>>(d_vel, nx, ny, nz, nvar, c0, nb, T.dflat, T.tmp, fac,
-                                                   T.node, T.wnum, T.wden, T.rmax, ifunc, igr, kmax, d_t,
-                                                   cgbuf.p);
+    // DSURF_DISP_OTF = resident blocks per SM of the on-the-fly-stack kernel (8, 9, 10, 12); 0 = first generation
+    static const int otf = getenv("DSURF_DISP_OTF") ? atoi(getenv("DSURF_DISP_OTF")) : kDispOtfDefault;
+    if (otf > 0 && nvar > 1) {
+      const int nslots = kDispBlock / nvar + 2;
+      const size_t smo = (size_t)T.rmax * 8 + (size_t)5 * T.rmax * 4 + (size_t)nslots * (3 * T.rmax + 3 * nz) * 4;
+#define DISP_OTF_LAUNCH(MB)                                                                                        \
+  k_disp_columns_otf<MB><<<grid, kDispBlock, smo, st>>>(d_vel, nx, ny, nz, nvar, c0, nb, T.dflat, T.tmp, fac, T.node, \
+                                                        T.wnum, T.wden, T.rmax, ifunc, igr, kmax, d_t, cgbuf.p, nslots)
+      if (otf >= 12)
+        DISP_OTF_LAUNCH(12);
+      else if (otf >= 10)
+        DISP_OTF_LAUNCH(10);
+      else if (otf == 9)
+        DISP_OTF_LAUNCH(9);
+      else
+        DISP_OTF_LAUNCH(8);
+#undef DISP_OTF_LAUNCH
+    } else {
+      k_disp_columns<<<grid, kDispBlock, smem, st>>>(d_vel, nx, ny, nz, nvar, c0, nb, T.dflat, T.tmp, fac,
+                                                     T.node, T.wnum, T.wden, T.rmax, ifunc, igr, kmax, d_t,
+                                                     cgbuf.p);
+    }
     const long long nf = (long long)nb * kmax;
     k_disp_finish<<<(int)((nf + 127) / 128), 128, 0, st>>>(d_vel, nx, ny, nz, nvar, c0, nb, kmax, cgbuf.p,
                                                            d_pv, d_sen_vs, d_sen_vp, d_sen_rho);

@@ -530,3 +530,34 @@ def test_lsmr_fused_cluster_kernels_match_unfused(taipei):
     assert out["fused"]["itn"] == out["unfused"]["itn"] and out["fused"]["istop"] == out["unfused"]["istop"]
     xf, xu = np.array(out["fused"]["x"]), np.array(out["unfused"]["x"])
     assert np.abs(xf - xu).max() <= 1e-6 * np.abs(xu).max()
+
+
+@pytest.mark.parametrize("otf", ["8", "10", "12"])
+def test_dispersion_on_the_fly_stacks_bit_identical(small_problem, otf):
+    """Second-generation column kernel (k_disp_columns_otf: one base stack per column in shared memory, perturbed
+    layers recomputed on the fly) against the first generation (one stack per thread): identical bits for
+    every variant curve, Rayleigh group and Love phase (separate processes: the variant is chosen at first use)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, json, hashlib, numpy as np; sys.path.insert(0, %r)\n"
+        "from dsurftomo_b200 import api, inputs\n"
+        "pb = inputs.synthetic_problem(12, 3, 6, ('Rc', 'Rg', 'Lc', 'Lg'), nrecv=5, name='small_4types')\n"
+        "rng = np.random.default_rng(11)\n"
+        "vs = (pb.vsf * (1.0 + 0.04 * rng.standard_normal(pb.vsf.shape))).astype(np.float32)\n"
+        "h = hashlib.sha256()\n"
+        "for iwave, igr, t in ((2, 1, pb.tRg), (1, 0, pb.tLc), (2, 0, pb.tRc)):\n"
+        "    for a in api.depthkernel(pb.nx, pb.ny, pb.nz, vs, iwave, igr, len(t), t, pb.depz, pb.minthk):\n"
+        "        assert np.isfinite(a).all(); h.update(np.ascontiguousarray(a).tobytes())\n"
+        "print(h.hexdigest())\n"
+    ) % (ROOT,)
+    out = {}
+    for name, val in (("first", "0"), ("otf", otf)):
+        env = dict(os.environ, DSURF_DISP_OTF=val)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[name] = r.stdout.strip().splitlines()[-1]
+    assert out["first"] == out["otf"]
