@@ -684,7 +684,7 @@ __device__ __forceinline__ float pow5f(float x) { const float x2 = x * x; return
 // kernel A: column variants (depthkernel / caldespersion)
 // ------------------------------------------------------------------------------------------
 constexpr int kDispBlock = 64;
-constexpr int kDispOtfDefault = 0;  // see k_disp_columns_otf; set after the A/B measurement
+constexpr int kDispOtfDefault = 0;  // first generation: the on-the-fly variants measured 1.7-1.9x slower (see k_disp_columns_otf)
 
 __global__ void __launch_bounds__(kDispBlock)
 k_disp_columns(const float *__restrict__ vel, int nx, int ny, int nz, int nvar, int col0, int ncol_batch,
@@ -759,7 +759,11 @@ k_disp_columns(const float *__restrict__ vel, int nx, int ny, int nz, int nvar, 
 // 25.6 KB (one stack per thread) to ~2.5 KB (one base stack per column), so residency is set by registers
 // alone: MINB = 8 (128 registers, 16 warps/SM like the first generation), 9, 10 (96 registers, 20 warps) or
 // 12 (80 registers, 24 warps).  ncu of the first generation at cfg-3 scale: FP64 pipe 28 % busy, every warp
-// waiting on dependent fixed-latency DP chains (profiles/r01_disp_cfg3.md) -- more resident warps is the lever.
+// waiting on dependent fixed-latency DP chains (profiles/r01_disp_cfg3.md), so more resident warps looked like the
+// lever.  MEASURED (gpurun_out/s18_disp_ab.log, Rc, 17161 columns x 55 variants x 16 periods): first generation
+// 1.23 s; on-the-fly 2.36 s (MINB 8), 2.08 s (10), 2.24 s (12) -- bit-identical output, but the per-access hit test,
+// its divergence across the 55 variants of a warp and the spills at 96/80 registers cost more than the extra warps
+// return.  Kept as an opt-in (DSURF_DISP_OTF) with its parity test; not the default.
 template <int MINB>
 __global__ void __launch_bounds__(kDispBlock, MINB)
 k_disp_columns_otf(const float *__restrict__ vel, int nx, int ny, int nz, int nvar, int col0, int ncol_batch,
