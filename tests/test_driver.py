@@ -181,3 +181,59 @@ def test_driver_checkerboard_run(taipei, tmp_path):
     # the inversion moved the start model towards the checkerboard
     start = pb.vsf[: pb.nz - 1, 1:-1, 1:-1].ravel()
     assert np.abs(syn[:, 3] - want).mean() < np.abs(start - want).mean()
+
+
+def test_driver_reader_list_directed_edge_cases(tmp_path):
+    """List-directed input forms gfortran accepts in DSurfTomo.in / the data file: comma separators, D exponents,
+    period lists wrapped over several records, trailing comments, blank lines in the data file; and the reference's
+    STOP on a missing input file (main.f90:130-131)."""
+    _need_bin()
+    (tmp_path / "DSurfTomo.in").write_text(
+        "c\nc\nc\n"
+        "data.dat   c: data file\n"
+        "5, 6, 3    c: nx ny nz\n"
+        "25.2d0 , 121.35   c: origin\n"
+        "1.5D-2 0.017\n"
+        "4\n"
+        "4.0,1.0\n"
+        "3\n"
+        "0.5 2.8\n"
+        "2\n"
+        "0.2\n"
+        "3      c: kmaxRc\n"
+        "0.5 1.0\n"
+        "2.0    c: wrapped period list\n"
+        "0\n0\n0\n"
+        "0\n0.02\n3.0\n")
+    (tmp_path / "data.dat").write_text(
+        "# 25.18 121.37 1 2 0\n"
+        "25.17, 121.39, 1.25\n"
+        "\n"
+        "25.175 121.40 1.3d0\n"
+        "# 25.17 121.39 3 2 0\n"
+        "25.18 121.37 1.5\n")
+    (tmp_path / "MOD").write_text("0.0 0.5 1.0\n" + ("1.0 1.1 1.2 1.3 1.4\n" * 6 + "2.0 2.1 2.2 2.3 2.4\n" * 6 +
+                                                    "3.0 3.1 3.2 3.3 3.4\n" * 6))
+    dump = tmp_path / "p.bin"
+    r = subprocess.run([BIN, str(tmp_path / "DSurfTomo.in"), "--parse-only", str(dump), "--quiet"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(dump, "rb").read()
+    hdr = struct.unpack("12i", raw[:48])
+    assert hdr[:10] == (5, 6, 3, 4, 3, 3, 3, 0, 0, 0)          # nx ny nz nsrc kmax dall kmaxRc..Lg
+    fh = np.frombuffer(raw[48:96], np.float32)
+    assert fh[0] == np.float32(25.2) and fh[2] == np.float32(0.015) and fh[4] == 4.0 and fh[5] == 1.0
+    t = np.frombuffer(raw[104:104 + 24], np.float64)
+    assert np.array_equal(t, [0.5, 1.0, 2.0])
+    off = 104 + 24 + 4 * (2 * 4 * 3 + 2 * 4 * 4 * 3)          # periods, scxf/sczf, rcxf/rczf
+    ints = np.frombuffer(raw[off:off + 4 * (4 * 4 * 3 + 3)], np.int32)
+    nrc1, nsrc1 = ints[3 * 12:4 * 12].reshape(3, 4), ints[4 * 12:]
+    assert nsrc1.tolist() == [1, 0, 1] and nrc1[0, 0] == 2 and nrc1[2, 0] == 1
+    obst = np.frombuffer(raw[off + ints.nbytes:off + ints.nbytes + 12], np.float32)
+    pb_dist = inputs.delsph(np.float32((90 - np.float32(25.18)) * inputs.PI32 / np.float32(180)),
+                            np.float32(np.float32(121.37) * inputs.PI32 / np.float32(180)),
+                            np.float32((90 - np.float32(25.17)) * inputs.PI32 / np.float32(180)),
+                            np.float32(np.float32(121.39) * inputs.PI32 / np.float32(180)))
+    assert obst[0] == np.float32(pb_dist / np.float32(1.25))
+    r = subprocess.run([BIN, str(tmp_path / "missing.in")], capture_output=True, text=True)
+    assert r.returncode == 2 and "unable to open the inputfile" in r.stderr
