@@ -2,31 +2,30 @@
 // gridder (src/CalSurfG.f90:1460-1553), bsplrefine (:1562-1628), travel/fouds2/addtree/downtree/
 // updtree (:288-921) and the source-grid refinement orchestration of CalSurfG (:1193-1355).
 //
-// Design (round 1): EXACT-ORDER REPLAY.  The reference's fast-marching result depends on the
-// acceptance order (fouds2 overwrites a trial value instead of taking a min, the mixed-order
-// stencil is upgraded as neighbours become alive, updtree only sifts up -- SURVEY.md section 7,
-// hard part 1), so a tile-parallel fast-iterative sweep converges to a slightly different
-// field.  To guarantee bit-identical travel times (and therefore bit-identical ray cells) each
-// sweep is marched by ONE WARP in the reference's exact pop order, and the GPU is filled with
-// thousands of independent (period, source) sweeps:
-//   * the narrow-band binary heap keeps (key, node) pairs; its first kHeapSm entries live in
-//     shared memory, deeper levels in a per-sweep global slab (L1/L2 resident);
-//   * when a node is accepted, the four neighbours' mixed-order updates are evaluated
-//     concurrently: 8 lanes per neighbour fetch its 8-point stencil (one packed
-//     (time,status) 8-byte load each), 4 lanes per neighbour solve one quadrant each and a
-//     2-step warp-shuffle min-reduction yields the trial time; heap inserts/updates are then
-//     applied in the reference's order (x-1, x+1, z-1, z+1);
-//   * heap/state writes are performed redundantly by all lanes (same address, same value), so
-//     every lane observes its own program-order writes and no intra-warp fence is needed on
-//     the serial path.
+// EXACT-ORDER REPLAY.  The reference's fast-marching result depends on the acceptance order
+// (fouds2 overwrites a trial value instead of taking a min, the mixed-order stencil is upgraded as
+// neighbours become alive, updtree only sifts up, ties are broken by the heap layout -- SURVEY.md
+// section 7, hard part 1), and ray cell indices flip on 1-ulp differences of T.  Every sweep is
+// therefore marched in the reference's exact pop order, and the GPU is filled with thousands of
+// independent (period, source) sweeps.  Two stages per sweep:
+//   * k_refine: the refined source grid (<= 129 x 129, early exit), 16 lanes per sweep on packed
+//     (time, status) records with a shared-memory/global (key, node) heap; then the injection into
+//     the coarse grid.  ~1.5 % of the pops.
+//   * k_march_lps: the coarse grid, ONE LANE PER SWEEP (32 sweeps per warp, every sweep of a batch
+//     resident), one 32-bit word per node, lazy heap back-pointers -- eik_lps.cuh.  Round 1 marched
+//     the coarse grid with 16 lanes per sweep (k_eikonal3 below, DSURF_EIKONAL_V3=1): 75 % of its
+//     issue slots were scalar heap work executed 16 lanes wide and half of its DRAM store sectors
+//     were 4-byte back-pointer updates (profiles/r01_eikonal_v3_source_regions.md).
 // All fp32 arithmetic follows the reference's operand order (library built with --fmad=false);
 // sin(colatitude) factors come from host-side tables computed with the C library.
 //
-// Bound: dependency depth / L2 latency -- the algorithmic HBM bytes of a sweep are only
+// Bound: dependency depth / DRAM sector rate -- the algorithmic HBM bytes of a sweep are only
 // 8*(Nc + Nr); the roofline fraction is reported anyway.
+#include <algorithm>
 #include "../../include/dsurftomo_b200.h"
 #include "common.cuh"
 #include "plan.cuh"
+#include "eik_lps.cuh"
 
 namespace dsurf {
 
@@ -79,26 +78,7 @@ int launch_dice(cudaStream_t st, const Geom &g, const double *d_pv_map, float *d
 }
 
 // ---------------------------------------------------------------- K3: eikonal
-constexpr int kHeapSm = 1024;     // heap entries [1, kHeapSm) kept in shared memory per warp
 constexpr int kWarpsPerBlock = 8;
-
-struct Heap {
-  float *sk;
-  int *sn;
-  float *gk;
-  int *gn;
-  __device__ __forceinline__ float key(int p) const { return p < kHeapSm ? sk[p] : gk[p]; }
-  __device__ __forceinline__ int nod(int p) const { return p < kHeapSm ? sn[p] : gn[p]; }
-  __device__ __forceinline__ void set(int p, float k, int n) const {
-    if (p < kHeapSm) {
-      sk[p] = k;
-      sn[p] = n;
-    } else {
-      gk[p] = k;
-      gn[p] = n;
-    }
-  }
-};
 
 struct Grid {
   int2 *node;          // packed (ttn bits, nsts)
@@ -113,65 +93,6 @@ struct Grid {
     mdiv = (unsigned)((1ull << (32 + sdiv)) / (unsigned)nnz) + 1u;
   }
 };
-
-// sift-up from position tpc with (key,node): addtree (:768-805) / updtree (:894-921)
-__device__ __forceinline__ void sift_up(const Heap &H, const Grid &G, int tpc, float key, int xn) {
-  int tpp = tpc >> 1;
-  while (tpp > 0) {
-    const float pk = H.key(tpp);
-    if (key < pk) {
-      const int pn = H.nod(tpp);
-      H.set(tpc, pk, pn);
-      G.node[pn].y = tpc;
-      tpc = tpp;
-      tpp = tpc >> 1;
-    } else {
-      tpp = 0;
-    }
-  }
-  H.set(tpc, key, xn);
-  G.node[xn].y = tpc;
-}
-
-// downtree (:816-885); the root has already been marked alive by the caller
-__device__ __forceinline__ void pop_root(const Heap &H, const Grid &G, int &ntr) {
-  if (ntr == 1) {
-    ntr = 0;
-    return;
-  }
-  const float mk = H.key(ntr);
-  const int mn = H.nod(ntr);
-  ntr = ntr - 1;
-  int tpp = 1, tpc = 2;
-  while (tpc < ntr) {
-    const float k1 = H.key(tpc), k2 = H.key(tpc + 1);
-    float kc = k1;
-    if (k1 > k2) {
-      tpc = tpc + 1;
-      kc = k2;
-    }
-    if (kc < mk) {
-      const int cn = H.nod(tpc);
-      H.set(tpp, kc, cn);
-      G.node[cn].y = tpp;
-      tpp = tpc;
-      tpc = 2 * tpp;
-    } else {
-      tpc = ntr + 1;
-    }
-  }
-  if (tpc == ntr) {
-    const float kc = H.key(tpc);
-    if (kc < mk) {
-      const int cn = H.nod(tpc);
-      H.set(tpp, kc, cn);
-      G.node[cn].y = tpp;
-      tpp = tpc;
-    }
-  }
-  H.set(tpp, mk, mn);
-  G.node[mn].y = tpp;
-}
 
 // one quadrant of fouds2 (:664-756): returns true and the trial time if a solution exists
 __device__ __forceinline__ bool quadrant(float Tj, float Tj2, int Sj, int Sj2, float Tk, float Tk2,
@@ -262,115 +183,6 @@ __device__ __forceinline__ bool quadrant(float Tj, float Tj2, int Sj, int Sj2, f
 
 constexpr int kOut = -9;  // status sentinel for "outside the grid"
 
-// the march loop of travel (:386-486).  REFINED adds the refined-grid exit test (:392-412).
-template <bool REFINED>
-__device__ int march(const Grid &G, const Heap &H, int ntr, int hcap, int lane, int vnl, int vnr,
-                     int vnt, int vnb) {
-  const int nnx = G.nnx, nnz = G.nnz;
-  const int grp = lane >> 3, q = lane & 7;
-  while (ntr > 0) {
-    const int root = H.nod(1);
-    const int ix = root / nnz + 1, iz = root - (ix - 1) * nnz + 1;
-    if (REFINED) {
-      int swrg = 0;
-      if (ix == 1 && vnl != 1) swrg = 1;
-      if (ix == nnx && vnr != nnx) swrg = 1;  // sic: the reference compares with the REFINED nnx
-      if (iz == 1 && vnt != 1) swrg = 1;
-      if (iz == nnz && vnb != nnz) swrg = 1;
-      if (swrg) {
-        G.node[root].y = 0;
-        break;
-      }
-    }
-    G.node[root].y = 0;
-    pop_root(H, G, ntr);
-    // ---- neighbour X of this lane group and the stencil node of this lane
-    int xx = ix, xz = iz;
-    if (grp == 0) xx = ix - 1;
-    if (grp == 1) xx = ix + 1;
-    if (grp == 2) xz = iz - 1;
-    if (grp == 3) xz = iz + 1;
-    const bool xin = (xx >= 1 && xx <= nnx && xz >= 1 && xz <= nnz);
-    const int xidx = (xx - 1) * nnz + (xz - 1);
-    int sx = xx, sz = xz;
-    {
-      const int off = (q & 1) ? 2 : 1;
-      const int sgn = (q & 2) ? 1 : -1;
-      if (q < 4)
-        sx = xx + sgn * off;
-      else
-        sz = xz + sgn * off;
-    }
-    const bool sin_ = xin && (sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz);
-    int2 sn = make_int2(0, kOut);
-    if (sin_) sn = G.node[(sx - 1) * nnz + (sz - 1)];
-    int2 xn = make_int2(0, 0);
-    float slown = 0.0f, risti = 0.0f;
-    if (xin) {
-      xn = G.node[xidx];
-      slown = 1.0f / G.vel[xidx];
-      risti = G.risti[xx - 1];
-    }
-    const int proc = (xin && xn.y != 0) ? (xn.y == -1 ? 1 : 2) : 0;
-    // ---- quadrant lanes: r = q (0..3): jside = r>>1, kside = r&1
-    const int gb = lane & ~7;
-    const int r = q & 3;
-    const int lj = gb + 2 * (r >> 1), lk = gb + 4 + 2 * (r & 1);
-    const float Tj = __int_as_float(__shfl_sync(kFull, sn.x, lj));
-    const float Tj2 = __int_as_float(__shfl_sync(kFull, sn.x, lj + 1));
-    const int Sj = __shfl_sync(kFull, sn.y, lj);
-    const int Sj2 = __shfl_sync(kFull, sn.y, lj + 1);
-    const float Tk = __int_as_float(__shfl_sync(kFull, sn.x, lk));
-    const float Tk2 = __int_as_float(__shfl_sync(kFull, sn.x, lk + 1));
-    const int Sk = __shfl_sync(kFull, sn.y, lk);
-    const int Sk2 = __shfl_sync(kFull, sn.y, lk + 1);
-    float trav = 3.0e38f;
-    if (proc && q < 4 && Sj != kOut && Sk != kOut) {
-      float tq;
-      if (quadrant(Tj, Tj2, Sj, Sj2, Tk, Tk2, Sk, Sk2, slown, G.earth, risti, G.dnx, G.dnz, tq)) trav = tq;
-    }
-    trav = fminf(trav, __shfl_xor_sync(kFull, trav, 1));
-    trav = fminf(trav, __shfl_xor_sync(kFull, trav, 2));
-    // ---- apply in the reference's order: x-1, x+1, z-1, z+1
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-      const int pr = __shfl_sync(kFull, proc, 8 * g);
-      if (!pr) continue;
-      const float tv = __shfl_sync(kFull, trav, 8 * g);
-      const int xi = __shfl_sync(kFull, xidx, 8 * g);
-      G.node[xi].x = __float_as_int(tv);
-      if (pr == 1) {
-        ntr = ntr + 1;
-        if (ntr > hcap) return -1;
-        sift_up(H, G, ntr, tv, xi);
-      } else {
-        const int pos = G.node[xi].y;  // re-read: earlier sifts may have moved it
-        sift_up(H, G, pos, tv, xi);
-      }
-    }
-  }
-  return ntr;
-}
-
-
-// =============================================================================================
-// v2 march: same pop order and arithmetic as march<> above, restructured so that the dependent
-// memory round trips of one acceptance overlap:
-//   (1) the stencil loads of the four neighbours are issued BEFORE the root is popped (they only
-//       depend on the root's coordinates; the pop changes heap positions, never times or the
-//       alive/close/far category);
-//   (2) heap entries are single 8-byte (key,node) words; when the sift-down leaves the
-//       shared-memory levels, the next four levels below the current slot (2+4+8+16 entries) are
-//       fetched by 30 lanes in ONE round trip and the walk continues on registers via shuffles;
-//   (3) the ancestors of the (up to four) insert/update positions are fetched by 8 lanes each in
-//       one round trip; a three-entry write log keeps earlier inserts of the same acceptance
-//       coherent, and any sift that actually moves entries drops the rest of the acceptance to
-//       plain loads (rare: new trial times are almost always larger than their parents');
-//   (4) the moving element of the next pop (the last heap entry) is kept in registers whenever it
-//       is known (it is the entry appended last), or fetched together with (3).
-// Heap positions of neighbours moved by the pop itself are tracked in registers, so no status
-// re-read is needed.  Results are bit-identical to march<> (tests/test_gpu_parity.py runs both).
-// =============================================================================================
 template <int HS>
 struct Heap2 {
   int2 *sm;  // entries [1, HS)
@@ -385,280 +197,6 @@ struct Heap2 {
 };
 __device__ __forceinline__ float keyf(int2 e) { return __int_as_float(e.x); }
 
-template <bool REFINED, int HS>
-__device__ int march2(const Grid &G, const Heap2<HS> &H, int ntr, int hcap, int lane, int vnl, int vnr, int vnt,
-                      int vnb) {
-  const int nnx = G.nnx, nnz = G.nnz;
-  const int grp = lane >> 3, q = lane & 7;
-  int2 lastE = make_int2(0, 0);
-  bool lastOK = false;
-  while (ntr > 0) {
-    const int root = H.sm[1].y;
-    const int ix = root / nnz + 1, iz = root - (ix - 1) * nnz + 1;
-    if (REFINED) {
-      int swrg = 0;
-      if (ix == 1 && vnl != 1) swrg = 1;
-      if (ix == nnx && vnr != nnx) swrg = 1;  // sic: compared with the REFINED nnx (:399-401)
-      if (iz == 1 && vnt != 1) swrg = 1;
-      if (iz == nnz && vnb != nnz) swrg = 1;
-      if (swrg) {
-        G.node[root].y = 0;
-        break;
-      }
-    }
-    G.node[root].y = 0;
-    // ---- (1) stencil loads, issued before the pop
-    int xx = ix, xz = iz;
-    if (grp == 0) xx = ix - 1;
-    if (grp == 1) xx = ix + 1;
-    if (grp == 2) xz = iz - 1;
-    if (grp == 3) xz = iz + 1;
-    const bool xin = (xx >= 1 && xx <= nnx && xz >= 1 && xz <= nnz);
-    const int xidx = xin ? (xx - 1) * nnz + (xz - 1) : -1;
-    int sx = xx, sz = xz;
-    {
-      const int off = (q & 1) ? 2 : 1;
-      const int sgn = (q & 2) ? 1 : -1;
-      if (q < 4)
-        sx = xx + sgn * off;
-      else
-        sz = xz + sgn * off;
-    }
-    const bool sin_ = xin && (sx >= 1 && sx <= nnx && sz >= 1 && sz <= nnz);
-    int2 sn = make_int2(0, kOut);
-    if (sin_) sn = G.node[(sx - 1) * nnz + (sz - 1)];
-    int2 xn = make_int2(0, 0);
-    float velx = 1.0f, risti = 0.0f;
-    if (xin) {
-      xn = G.node[xidx];
-      velx = G.vel[xidx];
-      risti = G.risti[xx - 1];
-    }
-    // ids of the four neighbours, known to every lane (for tracking heap moves)
-    const int xid0 = (ix - 1 >= 1) ? (ix - 2) * nnz + (iz - 1) : -1;
-    const int xid1 = (ix + 1 <= nnx) ? ix * nnz + (iz - 1) : -1;
-    const int xid2 = (iz - 1 >= 1) ? (ix - 1) * nnz + (iz - 2) : -1;
-    const int xid3 = (iz + 1 <= nnz) ? (ix - 1) * nnz + iz : -1;
-    int xm0 = -1, xm1 = -1, xm2 = -1, xm3 = -1;  // new positions of neighbours moved by the pop
-#define TRACK_MOVE(nid, newpos)      \
-  {                                  \
-    if ((nid) == xid0) xm0 = (newpos); \
-    if ((nid) == xid1) xm1 = (newpos); \
-    if ((nid) == xid2) xm2 = (newpos); \
-    if ((nid) == xid3) xm3 = (newpos); \
-  }
-    // ---- (2) downtree (:816-885)
-    if (ntr == 1) {
-      ntr = 0;
-      lastOK = false;
-    } else {
-      const int2 m = lastOK ? lastE : H.get(ntr);
-      const float mk = keyf(m);
-      ntr = ntr - 1;
-      int tpp = 1, tpc = 2;
-      bool stop = false;
-      while (!stop && tpc < ntr && tpc + 1 < HS) {  // both children in shared memory
-        const int2 e1 = H.sm[tpc], e2 = H.sm[tpc + 1];
-        int2 ec = e1;
-        if (keyf(e1) > keyf(e2)) {
-          tpc = tpc + 1;
-          ec = e2;
-        }
-        if (keyf(ec) < mk) {
-          H.sm[tpp] = ec;
-          G.node[ec.y].y = tpp;
-          TRACK_MOVE(ec.y, tpp);
-          tpp = tpc;
-          tpc = 2 * tpp;
-        } else {
-          stop = true;
-        }
-      }
-      while (!stop && tpc <= ntr) {
-        if (tpc + 1 < HS) {  // single child inside shared memory (tpc == ntr)
-          const int2 e1 = H.sm[tpc];
-          if (keyf(e1) < mk) {
-            H.sm[tpp] = e1;
-            G.node[e1.y].y = tpp;
-            TRACK_MOVE(e1.y, tpp);
-            tpp = tpc;
-          }
-          stop = true;
-          break;
-        }
-        // fetch the four levels below tpp: level r (1..4), offset o -> lane (2^r - 2) + o
-        const int r = (lane < 2) ? 1 : (lane < 6) ? 2 : (lane < 14) ? 3 : (lane < 30) ? 4 : 0;
-        const int o = lane - ((1 << r) - 2);
-        const long long pos = ((long long)tpp << r) + o;
-        int2 e = make_int2(0x7f800000, -1);
-        if (r > 0 && pos <= ntr) e = H.get((int)pos);
-        const int base = tpp;
-        int rel = 0;
-        for (int lvl = 1; lvl <= 4; lvl++) {
-          const long long c0 = ((long long)base << lvl) + 2 * rel;  // left child of the current slot
-          if (c0 > ntr) {
-            stop = true;
-            break;
-          }
-          const int Lc = (1 << lvl) - 2 + 2 * rel;
-          const int k1 = __shfl_sync(kFull, e.x, Lc), n1 = __shfl_sync(kFull, e.y, Lc);
-          const int k2 = __shfl_sync(kFull, e.x, Lc + 1), n2 = __shfl_sync(kFull, e.y, Lc + 1);
-          int pick = 0;
-          if (c0 < ntr && __int_as_float(k1) > __int_as_float(k2)) pick = 1;
-          const int2 ec = pick ? make_int2(k2, n2) : make_int2(k1, n1);
-          if (keyf(ec) < mk) {
-            H.set(tpp, ec);
-            G.node[ec.y].y = tpp;
-            TRACK_MOVE(ec.y, tpp);
-            tpp = (int)c0 + pick;
-            rel = 2 * rel + pick;
-            if (c0 == ntr) {  // that was the single last child
-              stop = true;
-              break;
-            }
-          } else {
-            stop = true;
-            break;
-          }
-        }
-        tpc = 2 * tpp;
-      }
-      H.set(tpp, m);
-      G.node[m.y].y = tpp;
-      TRACK_MOVE(m.y, tpp);
-      lastOK = false;
-    }
-#undef TRACK_MOVE
-    // ---- quadrants (as in march<>)
-    const float slown = 1.0f / velx;
-    const int proc = (xin && xn.y != 0) ? (xn.y == -1 ? 1 : 2) : 0;
-    const int gb = lane & ~7;
-    const int rq = q & 3;
-    const int lj = gb + 2 * (rq >> 1), lk = gb + 4 + 2 * (rq & 1);
-    const float Tj = __int_as_float(__shfl_sync(kFull, sn.x, lj));
-    const float Tj2 = __int_as_float(__shfl_sync(kFull, sn.x, lj + 1));
-    const int Sj = __shfl_sync(kFull, sn.y, lj);
-    const int Sj2 = __shfl_sync(kFull, sn.y, lj + 1);
-    const float Tk = __int_as_float(__shfl_sync(kFull, sn.x, lk));
-    const float Tk2 = __int_as_float(__shfl_sync(kFull, sn.x, lk + 1));
-    const int Sk = __shfl_sync(kFull, sn.y, lk);
-    const int Sk2 = __shfl_sync(kFull, sn.y, lk + 1);
-    float trav = 3.0e38f;
-    if (proc && q < 4 && Sj != kOut && Sk != kOut) {
-      float tq;
-      if (quadrant(Tj, Tj2, Sj, Sj2, Tk, Tk2, Sk, Sk2, slown, G.earth, risti, G.dnx, G.dnz, tq)) trav = tq;
-    }
-    trav = fminf(trav, __shfl_xor_sync(kFull, trav, 1));
-    trav = fminf(trav, __shfl_xor_sync(kFull, trav, 2));
-    // ---- (3) planned heap positions + one-shot ancestor fetch
-    int pr[4], xi[4], ppos[4];
-    float tv[4];
-    int nfar = 0;
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-      pr[g] = __shfl_sync(kFull, proc, 8 * g);
-      tv[g] = __shfl_sync(kFull, trav, 8 * g);
-      xi[g] = __shfl_sync(kFull, xidx, 8 * g);
-      const int st = __shfl_sync(kFull, xn.y, 8 * g);
-      const int xm = (g == 0) ? xm0 : (g == 1) ? xm1 : (g == 2) ? xm2 : xm3;
-      ppos[g] = 0;
-      if (pr[g] == 1) {
-        nfar++;
-        ppos[g] = ntr + nfar;
-      } else if (pr[g] == 2) {
-        ppos[g] = (xm >= 0) ? xm : st;
-      }
-    }
-    const int mypos = (grp == 0) ? ppos[0] : (grp == 1) ? ppos[1] : (grp == 2) ? ppos[2] : ppos[3];
-    const int myanc = mypos >> (q + 1);
-    int2 anc = make_int2(0, -1);
-    if (myanc >= 1) anc = H.get(myanc);
-    int2 cand = make_int2(0, -1);  // candidate "last entry" for the next pop when nothing is appended
-    if (nfar == 0 && ntr >= 1) cand = H.get(ntr);
-    // ---- apply in the reference's order: x-1, x+1, z-1, z+1 (:424-486)
-    bool slow = false;
-    int ls0 = -1, ls1 = -1, ls2 = -1, ls3 = -1;
-    int2 le0 = make_int2(0, 0), le1 = le0, le2 = le0, le3 = le0;
-    int nl = 0;
-    bool appended = false;
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-      if (!pr[g]) continue;
-      const int xg = xi[g];
-      const float tvg = tv[g];
-      G.node[xg].x = __float_as_int(tvg);
-      int tpc;
-      if (pr[g] == 1) {
-        ntr = ntr + 1;
-        if (ntr > hcap) return -1;
-        tpc = ntr;
-      } else {
-        tpc = slow ? G.node[xg].y : ppos[g];
-      }
-      const bool use_pref = !slow && (tpc == ppos[g]);
-      int a = 0;
-      bool moved = false;
-      int tpp = tpc >> 1;
-      while (tpp > 0) {
-        int2 pe;
-        if (use_pref && a < 8) {
-          pe.x = __shfl_sync(kFull, anc.x, 8 * g + a);
-          pe.y = __shfl_sync(kFull, anc.y, 8 * g + a);
-          if (tpp == ls0) pe = le0;
-          if (tpp == ls1) pe = le1;
-          if (tpp == ls2) pe = le2;
-        } else {
-          pe = H.get(tpp);
-        }
-        if (tvg < keyf(pe)) {
-          H.set(tpc, pe);
-          G.node[pe.y].y = tpc;
-          tpc = tpp;
-          tpp = tpc >> 1;
-          a++;
-          moved = true;
-        } else {
-          tpp = 0;
-        }
-      }
-      const int2 ne = make_int2(__float_as_int(tvg), xg);
-      H.set(tpc, ne);
-      G.node[xg].y = tpc;
-      if (moved) {
-        slow = true;
-      } else {
-        if (nl == 0) { ls0 = tpc; le0 = ne; }
-        if (nl == 1) { ls1 = tpc; le1 = ne; }
-        if (nl == 2) { ls2 = tpc; le2 = ne; }
-        if (nl == 3) { ls3 = tpc; le3 = ne; }
-        nl++;
-      }
-      if (pr[g] == 1) {
-        appended = true;
-        lastE = ne;
-        lastOK = !moved;  // the entry sits at slot ntr unless it was sifted up
-      } else if (appended && moved) {
-        // a later sift that moves entries cannot touch slot ntr (it only shifts its own ancestors)
-      }
-    }
-    // ---- (4) moving element of the next pop
-    if (!appended) {
-      if (!slow && ntr >= 1) {
-        lastE = cand;
-        if (ntr == ls0) lastE = le0;
-        if (ntr == ls1) lastE = le1;
-        if (ntr == ls2) lastE = le2;
-        if (ntr == ls3) lastE = le3;
-        lastOK = true;
-      } else {
-        lastOK = false;
-      }
-    } else if (slow) {
-      lastOK = false;  // conservative: positions may have shifted
-    }
-  }
-  return ntr;
-}
 
 // sift-up for the (few) initial inserts of a pass, on the v2 heap layout
 template <int HS>
@@ -683,198 +221,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_fill_nodes(int2 *node, long long n) {
   const long long tot = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) node[i] = make_int2(0, -1);
-}
-
-// ---- uniform interface over the two heap layouts
-__device__ __forceinline__ void heap_init(Heap &H, float *smem, int w, const BatchView &bv, int slot) {
-  H.sk = smem + (size_t)w * 2 * kHeapSm;
-  H.sn = (int *)(H.sk + kHeapSm);
-  H.gk = bv.hkey + (size_t)slot * (bv.hcap + 1);
-  H.gn = bv.hnode + (size_t)slot * (bv.hcap + 1);
-}
-template <int HS>
-__device__ __forceinline__ void heap_init(Heap2<HS> &H, float *smem, int w, const BatchView &bv, int slot) {
-  H.sm = (int2 *)smem + (size_t)w * HS;
-  H.gm = bv.hent + (size_t)slot * (bv.hcap + 1);
-}
-__device__ __forceinline__ void heap_sift(const Heap &H, const Grid &G, int tpc, float key, int xn) {
-  sift_up(H, G, tpc, key, xn);
-}
-template <int HS>
-__device__ __forceinline__ void heap_sift(const Heap2<HS> &H, const Grid &G, int tpc, float key, int xn) {
-  sift_up2(H, G, tpc, key, xn);
-}
-template <bool REFINED>
-__device__ __forceinline__ int heap_march(const Grid &G, const Heap &H, int ntr, int hcap, int lane, int a, int b,
-                                          int c, int d) {
-  return march<REFINED>(G, H, ntr, hcap, lane, a, b, c, d);
-}
-template <bool REFINED, int HS>
-__device__ __forceinline__ int heap_march(const Grid &G, const Heap2<HS> &H, int ntr, int hcap, int lane, int a,
-                                          int b, int c, int d) {
-  return march2<REFINED, HS>(G, H, ntr, hcap, lane, a, b, c, d);
-}
-
-template <class HeapT, int MINB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
-k_eikonal(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
-          const float *__restrict__ velv_all, const float *__restrict__ risti_c, BatchView bv) {
-  extern __shared__ float smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * kWarpsPerBlock + w;
-  if (slot >= nsw) return;
-  HeapT H;
-  heap_init(H, smem, w, bv, slot);
-  SweepDesc d = sw[slot];
-  const size_t Nc = (size_t)g.nnx * g.nnz;
-  const float *veln = veln_all + (size_t)d.map * Nc;
-  const float *velv = velv_all + (size_t)d.map * g.nx * g.ny;
-  int2 *node = bv.node + (size_t)slot * Nc;
-  int2 *noder = bv.noder + (size_t)slot * kRefMax * kRefMax;
-  float *velr = bv.velr + (size_t)slot * kRefMax * kRefMax;
-  const int nrnx = d.nrnx, nrnz = d.nrnz;
-  // ---- bsplrefine (:1562-1628): refined velocities + reset refined node states
-  {
-    const int nrr = g.gd * kSgdl;  // 64 (40 for synthetic)
-    const int origx = (d.vnl - 1) * kSgdl + 1, origz = (d.vnt - 1) * kSgdl + 1;
-    const int ldv = g.nvx + 2;
-    for (int n = lane; n < nrnx * nrnz; n += 32) {
-      const int idm1 = n % nrnz + 1, idm2 = n / nrnz + 1;
-      const int st1 = idm1 + origz - 1, st2 = idm2 + origx - 1;
-      int i = (st1 - 1) / nrr + 1;
-      if (i > g.nvz - 1) i = g.nvz - 1;
-      const int k = st1 - nrr * (i - 1);
-      int j = (st2 - 1) / nrr + 1;
-      if (j > g.nvx - 1) j = g.nvx - 1;
-      const int l = st2 - nrr * (j - 1);
-      float ul[4], vk[4];
-      bspline4((float)(l - 1) / (float)nrr, ul);
-      bspline4((float)(k - 1) / (float)nrr, vk);
-      float s[4];
-#pragma unroll
-      for (int i1 = 0; i1 < 4; i1++) {
-        float t = 0.0f;
-#pragma unroll
-        for (int j1 = 0; j1 < 4; j1++) t = t + ul[j1] * velv[(i - 1 + i1) * ldv + (j - 1 + j1)];
-        s[i1] = vk[i1] * t;
-      }
-      velr[n] = s[0] + s[1] + s[2] + s[3];
-      noder[n] = make_int2(0, -1);
-    }
-  }
-  __syncwarp();
-  // ---- travel(x, z, urg=1) on the refined grid (:312-375): source cell + 4 corner times
-  Grid R;
-  R.node = noder;
-  R.vel = velr;
-  R.risti = bv.ristr + (size_t)slot * kRefMax;
-  R.nnx = nrnx;
-  R.nnz = nrnz;
-  R.dnx = g.drnx;
-  R.dnz = g.drnz;
-  R.earth = g.earth;
-  R.set_div();
-  int ntr = 0;
-  {
-    const int isx = d.tsx, isz = d.tsz;
-    float vss[2][2];
-    for (int i = 0; i < 2; i++)
-      for (int j = 0; j < 2; j++) vss[i][j] = velr[(isx - 1 + i) * nrnz + (isz - 1 + j)];
-    const float dsx = (d.scx - d.gorx) - (float)(isx - 1) * g.drnx;
-    const float dsz = (d.scz - d.gorz) - (float)(isz - 1) * g.drnz;
-    float vsrc = 0.0f;  // bilinear (:2328-2349)
-    for (int i = 0; i < 2; i++)
-      for (int j = 0; j < 2; j++) {
-        const float produ = (1.0f - fabsf(((float)i * g.drnx - dsx) / g.drnx)) *
-                            (1.0f - fabsf(((float)j * g.drnz - dsz) / g.drnz));
-        vsrc = vsrc + vss[i][j] * produ;
-      }
-    for (int i = 0; i < 2; i++)
-      for (int j = 0; j < 2; j++) {
-        const float ex = dsx - (float)i * g.drnx, ez = dsz - (float)j * g.drnz;
-        const float ds = sqrtf(ex * ex + ez * ez);
-        const float t0 = 2.0f * ds / (vss[i][j] + vsrc);
-        const int xi = (isx - 1 + i) * nrnz + (isz - 1 + j);
-        noder[xi].x = __float_as_int(t0);
-        ntr = ntr + 1;
-        heap_sift(H, R, ntr, t0, xi);
-      }
-  }
-  int rc = heap_march<true>(R, H, ntr, bv.hcap, lane, d.vnl, d.vnr, d.vnt, d.vnb);
-  if (rc < 0) {
-    if (lane == 0) sw[slot].status = DSURF_ERR_HEAP;
-    return;
-  }
-  __syncwarp();
-  // ---- map refined -> coarse (:1289-1303); coarse states were pre-filled with (0,-1)
-  const int bw = d.vnr - d.vnl + 1, bh = d.vnb - d.vnt + 1;
-  for (int n = lane; n < bw * bh; n += 32) {
-    const int cz = n % bh, cx = n / bh;  // offsets inside the box
-    const int2 rn = noder[(cx * kSgdl) * nrnz + cz * kSgdl];
-    int2 cn = make_int2(0, rn.y);
-    if (rn.y >= 0) cn.x = rn.x;
-    node[(size_t)(d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz)] = cn;
-  }
-  __syncwarp();
-  // ---- narrow-band completion (:1332-1349): alive with a far neighbour -> close
-  // (order-free: a node turned close is still "not far" for its neighbours)
-  for (int n = lane; n < bw * bh; n += 32) {
-    const int cz = n % bh, cx = n / bh;
-    const int k = d.vnl + cx, l = d.vnt + cz;  // 1-based (ix, iz)
-    const size_t o = (size_t)(k - 1) * g.nnz + (l - 1);
-    if (node[o].y == 0) {
-      bool far = false;
-      if (l - 1 >= 1 && node[o - 1].y == -1) far = true;
-      if (l + 1 <= g.nnz && node[o + 1].y == -1) far = true;
-      if (k - 1 >= 1 && node[o - g.nnz].y == -1) far = true;
-      if (k + 1 <= g.nnx && node[o + g.nnz].y == -1) far = true;
-      // the reference writes 1 in place; neighbours only test ".EQ.-1", so deferring is identical
-      if (far) node[o].y = -100;
-    }
-  }
-  __syncwarp();
-  for (int n = lane; n < bw * bh; n += 32) {
-    const int cz = n % bh, cx = n / bh;
-    const size_t o = (size_t)(d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz);
-    if (node[o].y == -100) node[o].y = 1;
-  }
-  __syncwarp();
-  // ---- travel(x, z, urg=2): rebuild the heap by scanning i=1..nnx, j=1..nnz (:341-347);
-  // only nodes of the refined box can be close.
-  Grid C;
-  C.node = node;
-  C.vel = veln;
-  C.risti = risti_c;
-  C.nnx = g.nnx;
-  C.nnz = g.nnz;
-  C.dnx = g.dnx;
-  C.dnz = g.dnz;
-  C.earth = g.earth;
-  C.set_div();
-  ntr = 0;
-  for (int cx = 0; cx < bw; cx++) {
-    for (int base = 0; base < bh; base += 32) {
-      const int cz = base + lane;
-      int st = 0;
-      float tt = 0.0f;
-      if (cz < bh) {
-        const int2 v = node[(size_t)(d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz)];
-        st = v.y;
-        tt = __int_as_float(v.x);
-      }
-      unsigned mask = __ballot_sync(kFull, st > 0);
-      while (mask) {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float key = __shfl_sync(kFull, tt, b);
-        const int xi = (d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + base + b);
-        ntr = ntr + 1;
-        heap_sift(H, C, ntr, key, xi);
-      }
-    }
-  }
-  rc = heap_march<false>(C, H, ntr, bv.hcap, lane, 0, 0, 0, 0);
-  if (rc < 0 && lane == 0) sw[slot].status = DSURF_ERR_HEAP;
 }
 
 
@@ -1248,32 +594,15 @@ __device__ int march3(const Grid &G, const Heap2<V3<kG>::HS> &H, int2 *scr, int 
   return err ? -1 : ntr;
 }
 
+
+// ---- stage 1 of a sweep, shared by both pipelines: bsplrefine (:1562-1628), the refined-grid source
+// cell (:312-375) and travel(urg=1) on the refined grid with its exit test (:386-412).
+// Returns true if the heap slab was too small.
 template <int kG, bool LAZY>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, V3<kG>::MINB)
-k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
-           const float *__restrict__ velv_all, const float *__restrict__ risti_c, BatchView bv) {
-  extern __shared__ float smem[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kNG = V3<kG>::NG, kHS3 = V3<kG>::HS;
-  const int gg = lane / kG, gl = lane % kG, gbase = gg * kG;
-  const unsigned gm = ((kG == 32) ? 0xffffffffu : ((1u << kG) - 1u)) << gbase;
-  const int slot = (blockIdx.x * kWarpsPerBlock + w) * kNG + gg;
-  const unsigned wmask = __ballot_sync(kFull, slot < nsw);  // lanes of this warp that own a sweep
-  if (slot >= nsw) return;
-  int2 *wbase = (int2 *)smem + (size_t)w * kNG * (kHS3 + kScr);
-  Heap2<kHS3> H;
-  H.sm = wbase + (size_t)gg * kHS3;
-  H.gm = bv.hent + (size_t)slot * (bv.hcap + 1);
-  int2 *scr = wbase + (size_t)kNG * kHS3 + (size_t)gg * kScr;
-  SweepDesc d = sw[slot];
-  const size_t Nc = (size_t)g.nnx * g.nnz;
-  const float *veln = veln_all + (size_t)d.map * Nc;
-  const float *velv = velv_all + (size_t)d.map * g.nx * g.ny;
-  int2 *node = bv.node + (size_t)slot * Nc;
-  int2 *noder = bv.noder + (size_t)slot * kRefMax * kRefMax;
-  float *velr = bv.velr + (size_t)slot * kRefMax * kRefMax;
+__device__ __forceinline__ bool refine_stage(const Geom &g, const SweepDesc &d, const float *velv, int2 *noder, float *velr,
+                                             const float *ristr, const Heap2<V3<kG>::HS> &H, int2 *scr, int hcap, int gl,
+                                             unsigned gm, int gbase, unsigned wmask) {
   const int nrnx = d.nrnx, nrnz = d.nrnz;
-  // ---- bsplrefine (:1562-1628)
   {
     const int nrr = g.gd * kSgdl;
     const int origx = (d.vnl - 1) * kSgdl + 1, origz = (d.vnt - 1) * kSgdl + 1;
@@ -1306,7 +635,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
   Grid R;
   R.node = noder;
   R.vel = velr;
-  R.risti = bv.ristr + (size_t)slot * kRefMax;
+  R.risti = ristr;
   R.nnx = nrnx;
   R.nnz = nrnz;
   R.dnx = g.drnx;
@@ -1321,7 +650,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
       for (int j = 0; j < 2; j++) vss[i][j] = velr[(isx - 1 + i) * nrnz + (isz - 1 + j)];
     const float dsx = (d.scx - d.gorx) - (float)(isx - 1) * g.drnx;
     const float dsz = (d.scz - d.gorz) - (float)(isz - 1) * g.drnz;
-    float vsrc = 0.0f;
+    float vsrc = 0.0f;  // bilinear (:2328-2349)
     for (int i = 0; i < 2; i++)
       for (int j = 0; j < 2; j++) {
         const float produ = (1.0f - fabsf(((float)i * g.drnx - dsx) / g.drnx)) *
@@ -1339,10 +668,42 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
         sift_up2(H, R, ntr, t0, xi);
       }
   }
-  int rc = march3<true, kG, LAZY>(R, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, d.vnl, d.vnr, d.vnt, d.vnb);
-  const bool failed = rc < 0;
+  const int rc = march3<true, kG, LAZY>(R, H, scr, ntr, hcap, gl, gm, gbase, wmask, d.vnl, d.vnr, d.vnt, d.vnb);
+  return rc < 0;
+}
+
+// ---- legacy single-kernel pipeline (round 1, DSURF_EIKONAL_V3=1): kG lanes march the coarse grid too,
+// on packed (time, status) 8-byte node records.  Kept as an A/B reference for the pipeline below.
+template <int kG, bool LAZY>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, V3<kG>::MINB)
+k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
+           const float *__restrict__ velv_all, const float *__restrict__ risti_c, BatchView bv) {
+  extern __shared__ float smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kNG = V3<kG>::NG, kHS3 = V3<kG>::HS;
+  const int gg = lane / kG, gl = lane % kG, gbase = gg * kG;
+  const unsigned gm = ((kG == 32) ? 0xffffffffu : ((1u << kG) - 1u)) << gbase;
+  const int slot = (blockIdx.x * kWarpsPerBlock + w) * kNG + gg;
+  const unsigned wmask = __ballot_sync(kFull, slot < nsw);  // lanes of this warp that own a sweep
+  if (slot >= nsw) return;
+  int2 *wbase = (int2 *)smem + (size_t)w * kNG * (kHS3 + kScr);
+  Heap2<kHS3> H;
+  H.sm = wbase + (size_t)gg * kHS3;
+  H.gm = bv.hent + (size_t)slot * bv.slab;
+  int2 *scr = wbase + (size_t)kNG * kHS3 + (size_t)gg * kScr;
+  SweepDesc d = sw[slot];
+  const size_t Nc = (size_t)g.nnx * g.nnz;
+  const float *veln = veln_all + (size_t)d.map * Nc;
+  const float *velv = velv_all + (size_t)d.map * g.nx * g.ny;
+  int2 *node = bv.node + (size_t)slot * Nc;
+  int2 *noder = bv.noder + (size_t)slot * kRefMax * kRefMax;
+  float *velr = bv.velr + (size_t)slot * kRefMax * kRefMax;
+  const int nrnz = d.nrnz;
+  const bool failed = refine_stage<kG, LAZY>(g, d, velv, noder, velr, bv.ristr + (size_t)slot * kRefMax, H, scr, bv.hcap,
+                                             gl, gm, gbase, wmask);
   if (failed && gl == 0) sw[slot].status = DSURF_ERR_HEAP;
   __syncwarp(gm);
+  // ---- map refined -> coarse (:1289-1303); coarse states were pre-filled with (0,-1)
   const int bw = d.vnr - d.vnl + 1, bh = d.vnb - d.vnt + 1;
   for (int n = gl; n < bw * bh; n += kG) {
     const int cz = n % bh, cx = n / bh;
@@ -1352,6 +713,8 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
     node[(size_t)(d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz)] = cn;
   }
   __syncwarp(gm);
+  // ---- narrow-band completion (:1332-1349): alive with a far neighbour -> close
+  // (order-free: a node turned close is still "not far" for its neighbours)
   for (int n = gl; n < bw * bh; n += kG) {
     const int cz = n % bh, cx = n / bh;
     const int k = d.vnl + cx, l = d.vnt + cz;
@@ -1362,7 +725,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
       if (l + 1 <= g.nnz && node[o + 1].y == -1) far = true;
       if (k - 1 >= 1 && node[o - g.nnz].y == -1) far = true;
       if (k + 1 <= g.nnx && node[o + g.nnz].y == -1) far = true;
-      if (far) node[o].y = -100;
+      if (far) node[o].y = -100;  // the reference writes 1 in place; neighbours only test ".EQ.-1"
     }
   }
   __syncwarp(gm);
@@ -1372,6 +735,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
     if (node[o].y == -100) node[o].y = 1;
   }
   __syncwarp(gm);
+  // ---- travel(x, z, urg=2): rebuild the heap by scanning i=1..nnx, j=1..nnz (:341-347)
   Grid C;
   C.node = node;
   C.vel = veln;
@@ -1382,7 +746,7 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
   C.dnz = g.dnz;
   C.earth = g.earth;
   C.set_div();
-  ntr = 0;
+  int ntr = 0;
   for (int cx = 0; cx < bw; cx++) {
     for (int base = 0; base < bh; base += kG) {
       const int cz = base + gl;
@@ -1405,107 +769,275 @@ k_eikonal3(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict_
     }
   }
   if (failed) ntr = 0;  // keep taking part in the warp-wide barriers of the coarse march
-  rc = march3<false, kG, LAZY>(C, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, 0, 0, 0, 0);
+  const int rc = march3<false, kG, LAZY>(C, H, scr, ntr, bv.hcap, gl, gm, gbase, wmask, 0, 0, 0, 0);
   if (rc < 0 && gl == 0) sw[slot].status = DSURF_ERR_HEAP;
 }
 
-constexpr int kHeapSm2 = 768;  // v2: 6 KB of heap per warp -> 4 blocks (32 warps) per SM
+// =============================================================================================
+// Round-2 pipeline: k_refine (refined grid, 16 lanes per sweep, as above) + k_march_lps (coarse
+// grid, ONE LANE PER SWEEP, eik_lps.cuh).
+//
+// k_refine ends with the injection of CalSurfG.f90:1289-1349 evaluated on a (<= 17 x 17) scratch
+// copy of the refined box: alive box nodes are written to the coarse word array as their time,
+// close ones (refined close nodes and alive nodes with a far neighbour) become SEEDS, listed in
+// the order travel(urg=2) inserts them (ix outer, iz inner, :341-347).
+// =============================================================================================
+constexpr int kBoxMax = (2 * kSgs + 1) * (2 * kSgs + 1);  // 289 coarse nodes in the refined box
 
-// sweeps that can be resident at once with the selected kernel variant (batches larger than this
-// run as several waves of equal duration, so the plan sizes its batches to a multiple of it)
-int eikonal_resident_sweeps() {
-  const bool v1 = getenv("DSURF_EIKONAL_V1") != nullptr, v2 = getenv("DSURF_EIKONAL_V2") != nullptr;
-  const char *gs = getenv("DSURF_EIKONAL_G");
-  const bool g8 = gs && atoi(gs) == 8;
-  int nb = 0;
-  int per_block = kWarpsPerBlock;
-  if (v1) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal<Heap, 1>, kWarpsPerBlock * 32,
-                                                  (size_t)kWarpsPerBlock * 2 * kHeapSm * sizeof(float));
-  } else if (v2) {
-    cudaFuncSetAttribute(k_eikonal<Heap2<kHeapSm2>, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)((size_t)kWarpsPerBlock * kHeapSm2 * sizeof(int2)));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal<Heap2<kHeapSm2>, 4>, kWarpsPerBlock * 32,
-                                                  (size_t)kWarpsPerBlock * kHeapSm2 * sizeof(int2));
-  } else if (g8) {
-    const size_t sm = (size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2);
-    cudaFuncSetAttribute(k_eikonal3<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<8, true>, kWarpsPerBlock * 32, sm);
-    per_block = kWarpsPerBlock * V3<8>::NG;
-  } else {
-    const size_t sm = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
-    cudaFuncSetAttribute(k_eikonal3<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<16, true>, kWarpsPerBlock * 32, sm);
-    per_block = kWarpsPerBlock * V3<16>::NG;
+template <int kG>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, V3<kG>::MINB)
+k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ velv_all, BatchView bv) {
+  extern __shared__ float smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kNG = V3<kG>::NG, kHS3 = V3<kG>::HS;
+  const int gg = lane / kG, gl = lane % kG, gbase = gg * kG;
+  const unsigned gm = ((kG == 32) ? 0xffffffffu : ((1u << kG) - 1u)) << gbase;
+  const int slot = (blockIdx.x * kWarpsPerBlock + w) * kNG + gg;
+  const unsigned wmask = __ballot_sync(kFull, slot < nsw);
+  if (slot >= nsw) return;
+  int2 *wbase = (int2 *)smem + (size_t)w * kNG * (kHS3 + kScr);
+  Heap2<kHS3> H;
+  H.sm = wbase + (size_t)gg * kHS3;
+  H.gm = bv.hent + (size_t)slot * bv.slab;
+  int2 *scr = wbase + (size_t)kNG * kHS3 + (size_t)gg * kScr;
+  SweepDesc d = sw[slot];
+  const size_t Nc = (size_t)g.nnx * g.nnz;
+  const float *velv = velv_all + (size_t)d.map * g.nx * g.ny;
+  unsigned *word = bv.word + (size_t)slot * Nc;
+  int2 *noder = bv.noder + (size_t)slot * kRefMax * kRefMax;
+  float *velr = bv.velr + (size_t)slot * kRefMax * kRefMax;
+  int2 *box = bv.box + (size_t)slot * kBoxMax;
+  int2 *seed = bv.seed + (size_t)slot * kBoxMax;
+  const int nrnz = d.nrnz;
+  const bool failed = refine_stage<kG, false>(g, d, velv, noder, velr, bv.ristr + (size_t)slot * kRefMax, H, scr, bv.hcap,
+                                              gl, gm, gbase, wmask);
+  if (failed) {
+    if (gl == 0) {
+      sw[slot].status = DSURF_ERR_HEAP;
+      bv.nseed[slot] = 0;
+    }
+    return;
   }
+  __syncwarp(gm);
+  const int bw = d.vnr - d.vnl + 1, bh = d.vnb - d.vnt + 1;
+  for (int n = gl; n < bw * bh; n += kG) {  // (:1289-1303)
+    const int cz = n % bh, cx = n / bh;
+    const int2 rn = noder[(cx * kSgdl) * nrnz + cz * kSgdl];
+    box[n] = make_int2(rn.y >= 0 ? rn.x : 0, rn.y);
+  }
+  __syncwarp(gm);
+  for (int n = gl; n < bw * bh; n += kG) {  // (:1332-1349); every coarse node outside the box is far
+    const int cz = n % bh, cx = n / bh;
+    const int k = d.vnl + cx, l = d.vnt + cz;
+    if (box[n].y == 0) {
+      bool far = false;
+      if (l - 1 >= 1 && (cz == 0 || box[n - 1].y == -1)) far = true;
+      if (l + 1 <= g.nnz && (cz == bh - 1 || box[n + 1].y == -1)) far = true;
+      if (k - 1 >= 1 && (cx == 0 || box[n - bh].y == -1)) far = true;
+      if (k + 1 <= g.nnx && (cx == bw - 1 || box[n + bh].y == -1)) far = true;
+      if (far) box[n].y = -100;
+    }
+  }
+  __syncwarp(gm);
+  int ns = 0;
+  for (int cx = 0; cx < bw; cx++) {
+    for (int base = 0; base < bh; base += kG) {
+      const int cz = base + gl;
+      int2 v = make_int2(0, -1);
+      if (cz < bh) v = box[cx * bh + cz];
+      const int xi = (d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz);
+      const bool close = (v.y > 0 || v.y == -100);
+      if (cz < bh && v.y == 0) word[xi] = (unsigned)v.x;
+      const unsigned mask = (__ballot_sync(gm, close) >> gbase) & ((1u << kG) - 1u);
+      if (close) seed[ns + __popc(mask & ((1u << gl) - 1u))] = make_int2(v.x, xi);
+      ns += __popc(mask);
+    }
+  }
+  if (gl == 0) bv.nseed[slot] = ns;
+}
+
+constexpr int kLpsHS = 128;  // heap slots [1, 128) of every sweep live in shared memory, interleaved by sweep
+
+// Heap slots >= kLpsHS live in a per-sweep global slab laid out in 128-byte blocks: block(q) holds
+// the 2 + 4 + 8 descendants of slot q at relative depths 1..3, for q on levels 6, 9, 12, ...  A
+// sift-down arriving at such a slot finds the next three levels in one line; the two children of a
+// slot are adjacent (one 16-byte load).
+__host__ __device__ __forceinline__ int lps_gaddr(int p) {
+#if defined(__CUDA_ARCH__)
+  const int lvl = 31 - __clz(p);
+#else
+  const int lvl = 31 - __builtin_clz((unsigned)p);
+#endif
+  const int gi = (lvl - 7) / 3, Lp = 6 + 3 * gi, d = lvl - Lp;
+  const int parent = p >> d;
+  const int blk = ((1 << Lp) - 64) / 7 + (parent - (1 << Lp));
+  return blk * 16 + (1 << d) - 2 + (p - (parent << d));
+}
+int lps_slab_entries(int hcap) {
+  if (hcap < kLpsHS) return 16;
+  const int lvl = 31 - __builtin_clz((unsigned)hcap);
+  const int gi = (lvl - 7) / 3, Lp = 6 + 3 * gi;
+  return (((1 << Lp) - 64) / 7 + (1 << Lp)) * 16;
+}
+
+constexpr int kLpsLanes = 4;                   // lanes per sweep: lane g owns neighbour g of the accepted node
+constexpr int kLpsPerWarp = 32 / kLpsLanes;    // 8 sweeps per warp
+constexpr int kLpsWarps = 2;                   // warps per block
+
+struct LpsMem {
+  unsigned *w;
+  const float *v;
+  const float *ris;
+  int2 *sm;  // + sweep-in-warp; slot p at sm[p * kLpsPerWarp]: the 8 sweeps of a warp never share a bank pair
+  int2 *gm;
+  unsigned gmask;  // the four lanes of this sweep
+  int gbase, me;
+  static constexpr int kLanes = kLpsLanes;
+  static constexpr int kLg = 7;  // 2^7 = kLpsHS
+  __device__ __forceinline__ int lane() const { return me; }
+  template <class T>
+  __device__ __forceinline__ T bcast(T x, int src) const { return __shfl_sync(gmask, x, gbase + src); }
+  __device__ __forceinline__ bool any(bool p) const { return __any_sync(kFull, p); }
+  __device__ __forceinline__ uint32_t word(int i) const { return w[i]; }
+  __device__ __forceinline__ void set_word(int i, uint32_t x) const { w[i] = x; }
+  __device__ __forceinline__ float vel(int i) const { return __ldg(v + i); }
+  __device__ __forceinline__ float risti(int ix) const { return __ldg(ris + ix); }
+  __device__ __forceinline__ lps::Ent hget(int p) const {
+    const int2 e = (p < kLpsHS) ? sm[p * kLpsPerWarp] : gm[lps_gaddr(p)];
+    lps::Ent r;
+    r.x = e.x;
+    r.y = e.y;
+    return r;
+  }
+  __device__ __forceinline__ void hget2(int p, lps::Ent &a, lps::Ent &b) const {  // p even, both slots valid
+    if (p < kLpsHS) {
+      const int2 e1 = sm[p * kLpsPerWarp], e2 = sm[(p + 1) * kLpsPerWarp];
+      a.x = e1.x; a.y = e1.y; b.x = e2.x; b.y = e2.y;
+    } else {
+      const int4 e = *reinterpret_cast<const int4 *>(gm + lps_gaddr(p));
+      a.x = e.x; a.y = e.y; b.x = e.z; b.y = e.w;
+    }
+  }
+  __device__ __forceinline__ void hset(int p, lps::Ent e) const {
+    if (p < kLpsHS)
+      sm[p * kLpsPerWarp] = make_int2(e.x, e.y);
+    else
+      gm[lps_gaddr(p)] = make_int2(e.x, e.y);
+  }
+  __device__ __forceinline__ void stat(int, int) const {}
+  // block(q): the 14 descendants of slot q (q >= 64 on a level 6 + 3k) at relative depths 1..3 -- one 128-byte line
+  __device__ __forceinline__ void hblock(int q, lps::Ent b[14]) const {
+    const int Lp = 31 - __clz(q);
+    const int blk = ((1 << Lp) - 64) / 7 + (q - (1 << Lp));
+    const int4 *src = reinterpret_cast<const int4 *>(gm + (size_t)blk * 16);
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      const int4 v = src[i];
+      b[2 * i].x = v.x; b[2 * i].y = v.y; b[2 * i + 1].x = v.z; b[2 * i + 1].y = v.w;
+    }
+  }
+};
+static_assert(kLpsHS == (1 << LpsMem::kLg), "shared-memory heap levels");
+
+__global__ void __launch_bounds__(kLpsWarps * 32)
+k_march_lps(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
+            const float *__restrict__ risti_c, BatchView bv) {
+  extern __shared__ int2 lsm[];
+  const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / kLpsLanes;
+  const int slot = (blockIdx.x * kLpsWarps + wp) * kLpsPerWarp + grp;
+  const bool valid = slot < nsw;
+  const size_t Nc = (size_t)g.nnx * g.nnz;
+  LpsMem m;
+  m.me = lane % kLpsLanes;
+  m.gbase = grp * kLpsLanes;
+  m.gmask = ((1u << kLpsLanes) - 1u) << m.gbase;
+  m.sm = lsm + (size_t)wp * kLpsHS * kLpsPerWarp + grp;
+  m.ris = risti_c;
+  m.w = nullptr;
+  m.v = nullptr;
+  m.gm = nullptr;
+  int ntr = 0;
+  if (valid) {
+    m.w = bv.word + (size_t)slot * Nc;
+    m.v = veln_all + (size_t)sw[slot].map * Nc;
+    m.gm = bv.hent + (size_t)slot * bv.slab;
+    const int ns = bv.nseed[slot];
+    const int2 *seed = bv.seed + (size_t)slot * kBoxMax;
+    for (int i = 0; i < ns; i++) {  // travel(urg=2)'s addtree scan (:341-347); the four lanes write the same values
+      const int2 s = seed[i];
+      bool moved;
+      ntr = ntr + 1;
+      const int pos = lps::sift_up(m, ntr, __int_as_float(s.x), s.y, moved);
+      m.set_word(s.y, lps::kCloseBit | (uint32_t)pos);
+    }
+  }
+  lps::GridP G;
+  G.nnx = g.nnx;
+  G.nnz = g.nnz;
+  G.dnx = g.dnx;
+  G.dnz = g.dnz;
+  G.earth = g.earth;
+  const int rc = lps::march(G, m, ntr, bv.hcap);
+  if (valid && rc < 0 && m.me == 0) sw[slot].status = DSURF_ERR_HEAP;
+}
+
+static bool legacy_v3() {
+  static const bool v = getenv("DSURF_EIKONAL_V3") != nullptr;
+  return v;
+}
+bool eikonal_uses_words() { return !legacy_v3(); }
+
+// bytes of per-sweep heap slab (in int2 entries) the selected pipeline needs for capacity hcap
+int eikonal_slab_entries(int hcap) { return std::max(hcap + 1, legacy_v3() ? 0 : lps_slab_entries(hcap)); }
+
+// legacy pipeline: sweeps that can be resident at once (its batches are sized to whole waves);
+// the lane-per-sweep pipeline keeps every sweep of a batch resident and is limited by memory only
+int eikonal_resident_sweeps() {
+  if (!legacy_v3()) return 0;
+  const size_t sm = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
+  int nb = 0;
+  cudaFuncSetAttribute(k_eikonal3<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_eikonal3<16, false>, kWarpsPerBlock * 32, sm);
   cudaGetLastError();
   if (nb < 1) nb = 1;
-  return nb * per_block * sm_count();
+  return nb * kWarpsPerBlock * V3<16>::NG * sm_count();
 }
 
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
                    const float *d_velv_all, const float *d_risti, BatchView bv, int *launches) {
   if (nsw <= 0) return DSURF_OK;
   const long long ntot = (long long)nsw * g.nnx * g.nnz;
-  k_fill_nodes<<<sm_count() * 8, kWarpsPerBlock * 32, 0, st>>>(bv.node, ntot);
-  static const bool use_v1 = getenv("DSURF_EIKONAL_V1") != nullptr;  // reference variants for A/B tests
-  static const bool use_v2 = getenv("DSURF_EIKONAL_V2") != nullptr;
-  static const char *gsel = getenv("DSURF_EIKONAL_G");  // lanes per sweep of the v3 kernel: 16 (default) or 8
-  if (!use_v1 && !use_v2) {
-    const bool g8 = gsel && atoi(gsel) == 8;
-    const int ng = g8 ? V3<8>::NG : V3<16>::NG;
-    const int hs = g8 ? V3<8>::HS : V3<16>::HS;
-    const size_t smem = (size_t)kWarpsPerBlock * ng * (hs + kScr) * sizeof(int2);
-    // lazy heap back-pointers (see march3): measured 6 % SLOWER than the eager scheme at cfg 3 (the kernel is
-    // issue-bound, and a slot search by one sweep of a warp stalls the other), so eager is the default
-    static const bool eager = getenv("DSURF_EIKONAL_LAZY") == nullptr;
-    static bool attr3 = false;
-    if (!attr3) {
-      const int s8 = (int)((size_t)kWarpsPerBlock * V3<8>::NG * (V3<8>::HS + kScr) * sizeof(int2));
-      const int s16 = (int)((size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2));
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
-      attr3 = true;
-    }
-    const int per_block = kWarpsPerBlock * ng;
-    const int grid3 = (nsw + per_block - 1) / per_block;
-    SweepDesc *sw = const_cast<SweepDesc *>(d_sw);
-    const int nt = kWarpsPerBlock * 32;
-    if (g8 && eager)
-      k_eikonal3<8, false><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
-    else if (g8)
-      k_eikonal3<8, true><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
-    else if (eager)
-      k_eikonal3<16, false><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
-    else
+  SweepDesc *sw = const_cast<SweepDesc *>(d_sw);
+  const int nt = kWarpsPerBlock * 32;
+  const int per_block = kWarpsPerBlock * V3<16>::NG;
+  const int grid3 = (nsw + per_block - 1) / per_block;
+  const size_t smem = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
+  static bool attr = false;
+  if (!attr) {
+    DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DS_CUDA(cudaFuncSetAttribute(k_refine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DS_CUDA(cudaFuncSetAttribute(k_march_lps, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  if (legacy_v3()) {
+    k_fill_nodes<<<sm_count() * 8, nt, 0, st>>>(bv.node, ntot);
+    static const bool lazy = getenv("DSURF_EIKONAL_LAZY") != nullptr;
+    if (lazy)
       k_eikonal3<16, true><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
+    else
+      k_eikonal3<16, false><<<grid3, nt, smem, st>>>(g, sw, nsw, d_veln_all, d_velv_all, d_risti, bv);
     DS_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
     return DSURF_OK;
   }
-  const int grid = (nsw + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  if (use_v1) {
-    const size_t smem = (size_t)kWarpsPerBlock * 2 * kHeapSm * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal<Heap, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
-    k_eikonal<Heap, 1><<<grid, kWarpsPerBlock * 32, smem, st>>>(g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all,
-                                                                d_velv_all, d_risti, bv);
-  } else {
-    const size_t smem = (size_t)kWarpsPerBlock * kHeapSm2 * sizeof(int2);
-    static bool attr = false;
-    if (!attr) {
-      DS_CUDA(cudaFuncSetAttribute(k_eikonal<Heap2<kHeapSm2>, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-      attr = true;
-    }
-    k_eikonal<Heap2<kHeapSm2>, 4><<<grid, kWarpsPerBlock * 32, smem, st>>>(
-        g, const_cast<SweepDesc *>(d_sw), nsw, d_veln_all, d_velv_all, d_risti, bv);
-  }
+  DS_CUDA(cudaMemsetAsync(bv.word, 0xFF, (size_t)ntot * sizeof(unsigned), st));  // every node far
+  k_refine<16><<<grid3, nt, smem, st>>>(g, sw, nsw, d_velv_all, bv);
+  DS_CUDA(cudaGetLastError());
+  const int per_blk = kLpsWarps * kLpsPerWarp;
+  k_march_lps<<<(nsw + per_blk - 1) / per_blk, kLpsWarps * 32, (size_t)kLpsWarps * kLpsHS * kLpsPerWarp * sizeof(int2), st>>>(
+      g, sw, nsw, d_veln_all, d_risti, bv);
   DS_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   return DSURF_OK;

@@ -82,9 +82,11 @@ struct dsurf_plan {
   std::vector<int> S_id_base = std::vector<int>(4, 0);
   // batch workspace
   int maxslots = 0, maxrays = 0, hcap = 0;
-  DevBuf<int2> node, noder;
-  DevBuf<float> velr, hkey, ristr;
-  DevBuf<int> hnode;
+  bool words = true;          // node state: one word per node (eik_lps.cuh) or legacy (time, status) records
+  DevBuf<int2> node, noder, box, seed;
+  DevBuf<unsigned> word;
+  DevBuf<int> nseed;
+  DevBuf<float> velr, ristr;
   DevBuf<int2> hent;
   DevBuf<SweepDesc> d_sw;
   DevBuf<RayDesc> d_rays;
@@ -328,32 +330,65 @@ static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const floa
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
   p->hcap = 8 * (p->g.nnx + p->g.nnz) + 1024;
+  if (eikonal_uses_words()) {
+    // the blocked heap slab (eikonal.cu: lps_gaddr) is allocated in whole level groups: capacities 2^(10+3k) - 1.
+    // Measured narrow bands at 1025^2: mean 1.8-2.8 k, max 4.1 k entries (tests/host/lps_host_check.cpp).
+    int cap = 1023;
+    while (cap < 2 * (p->g.nnx + p->g.nnz)) cap = cap * 8 + 7;
+    p->hcap = cap;
+  }
+  {
+    const long long maxbt = (long long)std::lround(0.5 * (double)p->g.nnx * p->g.nnz);  // the reference's limit (:1093)
+    if (p->hcap > maxbt) p->hcap = (int)std::max<long long>(maxbt, 16);
+  }
   if (const char *hc = getenv("DSURF_HCAP")) p->hcap = std::max(16, atoi(hc));  // test hook: force heap-slab growth
   const size_t fdm_per_ray = forward_only ? sizeof(float) : (size_t)(p->g.nvz + 2) * (p->g.nvx + 2) * sizeof(float);
   int maxnrc = 1;
   for (auto &gi : p->gathers) maxnrc = std::max(maxnrc, gi.nrc);
-  const size_t per_slot = Nc * sizeof(int2) + (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) +
-                          (size_t)(p->hcap + 1) * 16 + kRefMax * sizeof(float) + sizeof(SweepDesc) +
-                          (size_t)maxnrc * (fdm_per_ray + sizeof(RayDesc) + 64);
-  const size_t budget = std::min<size_t>((size_t)(freeb * 0.6), (size_t)100 << 30);
-  long long nsw_total = 0;
-  for (auto &gi : p->gathers) nsw_total += (gi.igr == 1 && !forward_only) ? 2 : 1;
+  p->words = eikonal_uses_words();
+  const size_t slab = (size_t)eikonal_slab_entries(p->hcap);
+  const size_t kBox = (size_t)(2 * kSgs + 1) * (2 * kSgs + 1);
+  const size_t per_slot = Nc * (p->words ? sizeof(unsigned) : sizeof(int2)) +
+                          (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) + slab * sizeof(int2) +
+                          kRefMax * sizeof(float) + sizeof(SweepDesc) + kBox * 2 * sizeof(int2) + sizeof(int);
+  // rays are traced and assembled in chunks of at most maxrays (their dense fdm slabs dominate otherwise)
+  const size_t per_ray = fdm_per_ray + sizeof(RayDesc) + 64;
+  long long nsw_total = 0, nray_total = 0;
+  for (auto &gi : p->gathers) {
+    const int ns = (gi.igr == 1 && !forward_only) ? 2 : 1;
+    nsw_total += ns;
+    nray_total += (long long)ns * gi.nrc;
+  }
+  long long mr = std::max<long long>(4096, (long long)(((size_t)4 << 30) / per_ray));
+  mr = std::max<long long>(std::min<long long>(mr, nray_total), maxnrc);
+  if (const char *e = getenv("DSURF_MAXRAYS")) mr = std::max<long long>(maxnrc, atoll(e));  // test hook: force ray chunking
+  p->maxrays = (int)mr;
+  // the lane-per-sweep march wants every sweep resident at once: take what the device has, leaving room for the
+  // COO output and the LSMR system that follow
+  const size_t reserve_b = std::min<size_t>((size_t)40 << 30, freeb / 4);
+  size_t budget = freeb > reserve_b + mr * per_ray ? freeb - reserve_b - (size_t)mr * per_ray : freeb / 2;
+  if (!p->words) budget = std::min<size_t>((size_t)(freeb * 0.6), (size_t)100 << 30);
   long long ms = (long long)(budget / per_slot);
   ms = std::min<long long>(ms, std::max<long long>(nsw_total, 1));
-  {  // batches of at most one resident wave (larger launches would run as equal-length waves)
+  {  // legacy pipeline: batches of at most one resident wave (larger launches would run as equal-length waves)
     const long long res = eikonal_resident_sweeps();
     if (res > 0) ms = std::min<long long>(ms, res);
   }
+  if (const char *e = getenv("DSURF_MAXSLOTS")) ms = std::min<long long>(ms, std::max(1, atoi(e)));  // test hook: force batching
   ms = std::max<long long>(ms, 1);
   p->maxslots = (int)ms;
-  p->maxrays = (int)std::min<long long>((long long)p->maxslots * maxnrc, 1ll << 30);
   bad = false;
-  bad |= p->node.reserve((size_t)p->maxslots * Nc) != cudaSuccess;
+  if (p->words) {
+    bad |= p->word.reserve((size_t)p->maxslots * Nc) != cudaSuccess;
+    bad |= p->box.reserve((size_t)p->maxslots * kBox) != cudaSuccess;
+    bad |= p->seed.reserve((size_t)p->maxslots * kBox) != cudaSuccess;
+    bad |= p->nseed.reserve((size_t)p->maxslots) != cudaSuccess;
+  } else {
+    bad |= p->node.reserve((size_t)p->maxslots * Nc) != cudaSuccess;
+  }
   bad |= p->noder.reserve((size_t)p->maxslots * kRefMax * kRefMax) != cudaSuccess;
   bad |= p->velr.reserve((size_t)p->maxslots * kRefMax * kRefMax) != cudaSuccess;
-  bad |= p->hkey.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
-  bad |= p->hnode.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
-  bad |= p->hent.reserve((size_t)p->maxslots * (p->hcap + 1)) != cudaSuccess;
+  bad |= p->hent.reserve((size_t)p->maxslots * slab) != cudaSuccess;
   bad |= p->ristr.reserve((size_t)p->maxslots * kRefMax) != cudaSuccess;
   bad |= p->d_sw.reserve(p->maxslots) != cudaSuccess;
   bad |= p->d_rays.reserve(p->maxrays) != cudaSuccess;
@@ -616,7 +651,24 @@ static int write_paths(dsurf_plan *p, const std::vector<SweepDesc> &hsw, const s
   return DSURF_OK;
 }
 
-// runs one batch of sweeps (already described in hsw / hrays); assemble = false keeps fdm
+static BatchView batch_view(dsurf_plan *p) {
+  BatchView bv;
+  bv.node = p->node.p;
+  bv.word = p->words ? p->word.p : nullptr;
+  bv.box = p->box.p;
+  bv.seed = p->seed.p;
+  bv.nseed = p->nseed.p;
+  bv.slab = eikonal_slab_entries(p->hcap);
+  bv.noder = p->noder.p;
+  bv.velr = p->velr.p;
+  bv.hent = p->hent.p;
+  bv.ristr = p->ristr.p;
+  bv.hcap = p->hcap;
+  return bv;
+}
+
+// runs one batch of sweeps (already described in hsw / hrays); assemble = false keeps fdm.
+// Rays are traced and assembled in chunks of at most p->maxrays, in row order.
 static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<RayDesc> &hrays,
                      std::vector<float> &hristr, std::vector<int> &hrayS, std::vector<int> &hrayrow,
                      bool assemble, int *launches) {
@@ -625,22 +677,9 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
   cudaStream_t st = p->st;
   DS_CUDA(cudaMemcpyAsync(p->d_sw.p, hsw.data(), nsw * sizeof(SweepDesc), cudaMemcpyHostToDevice, st));
   DS_CUDA(cudaMemcpyAsync(p->ristr.p, hristr.data(), (size_t)nsw * kRefMax * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (nrays > 0) {
-    DS_CUDA(cudaMemcpyAsync(p->d_rays.p, hrays.data(), nrays * sizeof(RayDesc), cudaMemcpyHostToDevice, st));
-    DS_CUDA(cudaMemcpyAsync(p->ray_S.p, hrayS.data(), nrays * sizeof(int), cudaMemcpyHostToDevice, st));
-    DS_CUDA(cudaMemcpyAsync(p->ray_row.p, hrayrow.data(), nrays * sizeof(int), cudaMemcpyHostToDevice, st));
-  }
   float ms;
   for (int attempt = 0; attempt < 3; attempt++) {
-    BatchView bv;
-    bv.node = p->node.p;
-    bv.noder = p->noder.p;
-    bv.velr = p->velr.p;
-    bv.hkey = p->hkey.p;
-    bv.hnode = p->hnode.p;
-    bv.hent = p->hent.p;
-    bv.ristr = p->ristr.p;
-    bv.hcap = p->hcap;
+    const BatchView bv = batch_view(p);
     cudaEventRecord(p->ev[0], st);
     DS_CHECK(launch_eikonal(st, p->g, p->d_sw.p, nsw, p->veln_all.p, p->velv_all.p, p->risti_c.p, bv, launches));
     cudaEventRecord(p->ev[1], st);
@@ -660,38 +699,33 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
       set_error(__FILE__, __LINE__, "narrow-band heap exceeded maxbt = NINT(0.5*nnx*nnz)");
       return DSURF_ERR_HEAP;
     }
-    p->hcap = (int)std::min<long long>(maxbt, (long long)p->hcap * 8);
-    if (p->hkey.reserve((size_t)p->maxslots * (p->hcap + 1)) || p->hnode.reserve((size_t)p->maxslots * (p->hcap + 1)) ||
-        p->hent.reserve((size_t)p->maxslots * (p->hcap + 1))) {
+    p->hcap = (int)std::min<long long>(maxbt, (long long)p->hcap * 8 + 7);
+    if (p->hent.reserve((size_t)p->maxslots * (size_t)eikonal_slab_entries(p->hcap))) {
       set_error(__FILE__, __LINE__, "cudaMalloc failed (heap growth)");
       return DSURF_ERR_CUDA;
     }
     for (auto &s : hsw) s.status = 0;
     DS_CUDA(cudaMemcpyAsync(p->d_sw.p, hsw.data(), nsw * sizeof(SweepDesc), cudaMemcpyHostToDevice, st));
   }
-  if (nrays > 0) {
-    BatchView bv;
-    bv.node = p->node.p;
-    bv.noder = p->noder.p;
-    bv.velr = p->velr.p;
-    bv.hkey = p->hkey.p;
-    bv.hnode = p->hnode.p;
-    bv.hent = p->hent.p;
-    bv.ristr = p->ristr.p;
-    bv.hcap = p->hcap;
+  const bool want_paths = p->path_fh != nullptr && p->path_cap > 0;
+  for (int r0 = 0; r0 < nrays; r0 += p->maxrays) {
+    const int nr = std::min(p->maxrays, nrays - r0);
+    const BatchView bv = batch_view(p);
+    DS_CUDA(cudaMemcpyAsync(p->d_rays.p, hrays.data() + r0, nr * sizeof(RayDesc), cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemcpyAsync(p->ray_S.p, hrayS.data() + r0, nr * sizeof(int), cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemcpyAsync(p->ray_row.p, hrayrow.data() + r0, nr * sizeof(int), cudaMemcpyHostToDevice, st));
     cudaEventRecord(p->ev[2], st);
-    const bool want_paths = p->path_fh != nullptr && p->path_cap > 0;
-    if (want_paths && (p->path.reserve((size_t)nrays * p->path_cap) || p->path_n.reserve(nrays))) {
+    if (want_paths && (p->path.reserve((size_t)nr * p->path_cap) || p->path_n.reserve(nr))) {
       set_error(__FILE__, __LINE__, "cudaMalloc failed (ray-path export buffers)");
       return DSURF_ERR_CUDA;
     }
-    DS_CHECK(launch_rays(st, p->g, p->d_sw.p, p->d_rays.p, nrays, p->veln_all.p, bv, p->dsurf.p, p->fdm.p,
+    DS_CHECK(launch_rays(st, p->g, p->d_sw.p, p->d_rays.p, nr, p->veln_all.p, bv, p->dsurf.p, p->fdm.p,
                          p->bbox.p, p->flags.p + 1, p->flags.p, want_paths ? p->path.p : nullptr,
                          want_paths ? p->path_n.p : nullptr, p->path_cap));
     if (launches) *launches += 1;
     cudaEventRecord(p->ev[3], st);
     if (assemble) {
-      DS_CHECK(launch_assembly(st, p->g, p->nz, p->fdm.p, p->bbox.p, nrays, p->ray_S.p, p->S_ptr.p,
+      DS_CHECK(launch_assembly(st, p->g, p->nz, p->fdm.p, p->bbox.p, nr, p->ray_S.p, p->S_ptr.p,
                                p->S_stride.p, p->ray_row.p, p->cnt, p->wide, p->loff, p->roff, p->lpos, p->lval,
                                p->lcnt, p->tmp, p->rw, p->col, p->rowidx, p->nar, p->flags.p, launches));
     }
@@ -702,7 +736,10 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
     p->ms[3] += ms;
     cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]);
     p->ms[4] += ms;
-    if (want_paths) DS_CHECK(write_paths(p, hsw, hrays));
+    if (want_paths) {
+      std::vector<RayDesc> chunk(hrays.begin() + r0, hrays.begin() + r0 + nr);
+      DS_CHECK(write_paths(p, hsw, chunk));
+    }
   }
   return DSURF_OK;
 }
@@ -768,7 +805,7 @@ extern "C" int dsurf_plan_sweeps(dsurf_plan *p, int g0, int g1) {
     while (g < g1) {
       const GatherInfo &gi = p->gathers[g];
       const int ns = (gi.igr == 1 && !p->forward_only) ? 2 : 1;
-      if (!hsw.empty() && ((int)hsw.size() + ns > p->maxslots || (int)hrays.size() + ns * gi.nrc > p->maxrays)) break;
+      if (!hsw.empty() && (int)hsw.size() + ns > p->maxslots) break;
       DS_CHECK(append_gather(p, g, 0, hsw, hrays, hristr, hrayS, hrayrow));
       g++;
     }
@@ -846,7 +883,9 @@ extern "C" int dsurf_plan_debug_sweep(dsurf_plan *p, int gidx, int ig, float *ve
   const size_t Nc = (size_t)g.nnx * g.nnz;
   const SweepDesc &d = hsw[0];
   if (veln) DS_CUDA(cudaMemcpy(veln, p->veln_all.p + (size_t)d.map * Nc, Nc * sizeof(float), cudaMemcpyDeviceToHost));
-  if (ttn) {
+  if (ttn && p->words) {
+    DS_CUDA(cudaMemcpy(ttn, p->word.p, Nc * sizeof(float), cudaMemcpyDeviceToHost));  // every node alive: word = time
+  } else if (ttn) {
     std::vector<int2> tmp(Nc);
     DS_CUDA(cudaMemcpy(tmp.data(), p->node.p, Nc * sizeof(int2), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < Nc; i++) memcpy(&ttn[i], &tmp[i].x, 4);

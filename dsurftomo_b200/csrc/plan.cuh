@@ -70,12 +70,15 @@ struct RayDesc {              // one receiver of one sweep
 
 // per-sweep state of a batch slot (device pointers)
 struct BatchView {
-  int2 *node;        // [slot][nnx*nnz] packed (float bits of ttn, nsts), iz fastest
+  int2 *node;        // legacy pipeline: [slot][nnx*nnz] packed (float bits of ttn, nsts), iz fastest
+  unsigned *word;    // [slot][nnx*nnz] one word per coarse node (eik_lps.cuh); alive = fp32 time; null in legacy mode
+  int2 *box;         // [slot][289] injection scratch (status, time) of the refined box
+  int2 *seed;        // [slot][289] (key bits, node) of the coarse close nodes in travel(urg=2)'s insertion order
+  int *nseed;        // [slot]
+  int slab;          // int2 entries of heap slab per slot
   int2 *noder;       // [slot][129*129] refined (ttnr, nstsr), leading dimension nrnz
   float *velr;       // [slot][129*129] refined velocity
-  float *hkey;       // [slot][hcap+1] heap keys beyond the shared-memory part
-  int *hnode;        // [slot][hcap+1]
-  int2 *hent;        // [slot][hcap+1] (key,node) entries of the v2 heap layout
+  int2 *hent;        // [slot][slab] (key,node) heap entries beyond the shared-memory part
   const float *ristr; // [slot][129] earth*sin(gorx+(ix-1)*drnx), host libm
   int hcap;
 };
@@ -83,7 +86,9 @@ struct BatchView {
 int launch_dice(cudaStream_t st, const Geom &g, const double *d_pv_map, float *d_velv, float *d_veln);
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
                    const float *d_velv_all, const float *d_risti, BatchView bv, int *launches);
-int eikonal_resident_sweeps();
+int eikonal_resident_sweeps();        // legacy pipeline only; 0 = limited by memory only
+int eikonal_slab_entries(int hcap);
+bool eikonal_uses_words();
 int launch_rays(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, const RayDesc *d_rays, int nrays,
                 const float *d_veln_all, BatchView bv, float *d_tt, float *d_fdm, int4 *d_bbox,
                 int *d_rbint, int *d_err, float2 *d_path = nullptr, int *d_path_n = nullptr, int path_cap = 0);

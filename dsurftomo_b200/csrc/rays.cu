@@ -68,6 +68,13 @@ __device__ __forceinline__ float sin_cr(float y) {
 }
 
 __device__ __forceinline__ float node_t(const int2 *n, size_t i) { return __int_as_float(n[i].x); }
+// coarse travel times: one word per node (eik_lps.cuh; every node is alive after the sweep, word = time)
+// or the legacy packed (time, status) records
+struct CoarseT {
+  const int2 *n;
+  const unsigned *w;
+  __device__ __forceinline__ float t(size_t i) const { return w ? __uint_as_float(w[i]) : __int_as_float(n[i].x); }
+};
 
 // bilinear interpolation of velocity at (drx, drz) inside cell (ipz, ipx), guards as :2153-2157
 __device__ __forceinline__ float vel_at(const float *veln, int nnx, int nnz, int ipx, int ipz, float drx,
@@ -105,7 +112,9 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
   bbox[rid] = make_int4(1, 0, 1, 0);  // empty until the ray has been traced
   const size_t Nc = (size_t)g.nnx * g.nnz;
   const float *veln = veln_all + (size_t)d.map * Nc;
-  const int2 *node = bv.node + (size_t)rd.sweep * Nc;
+  CoarseT node;
+  node.n = bv.word ? nullptr : bv.node + (size_t)rd.sweep * Nc;
+  node.w = bv.word ? bv.word + (size_t)rd.sweep * Nc : nullptr;
   const int2 *noder = bv.noder + (size_t)rd.sweep * kRefMax * kRefMax;
   const int nnx = g.nnx, nnz = g.nnz, nnxr = d.nrnx, nnzr = d.nrnz;
   const float gox = g.gox, goz = g.goz, dnx = g.dnx, dnz = g.dnz, dvx = g.dvx, dvz = g.dvz;
@@ -157,7 +166,7 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
       for (int k = 0; k < 2; k++)
         for (int l = 0; l < 2; l++) {
           const float produ = (1.0f - fabsf(((float)l * dnz - drz) / dnz)) * (1.0f - fabsf(((float)k * dnx - drx) / dnx));
-          trr = trr + node_t(node, (size_t)(irx - 1 + k) * nnz + (irz - 1 + l)) * produ;
+          trr = trr + node.t((size_t)(irx - 1 + k) * nnz + (irz - 1 + l)) * produ;
         }
     }
     tt_out[rd.row] = trr;
@@ -223,8 +232,8 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
       dtz = dtz / (2.0f * earth * sinx * dnzr);
     } else {
       const size_t o = (size_t)(ipx - 1) * nnz + (ipz - 1);
-      const float t00 = node_t(node, o), t10 = node_t(node, o + 1);
-      const float t01 = node_t(node, o + nnz), t11 = node_t(node, o + nnz + 1);
+      const float t00 = node.t(o), t10 = node.t(o + 1);
+      const float t01 = node.t(o + nnz), t11 = node.t(o + nnz + 1);
       dtx = t01 - t00;
       dtx = dtx + t11 - t10;
       dtx = dtx / (2.0f * earth * dnx);

@@ -325,17 +325,21 @@ def test_device_glue_matches_host_glue(taipei):
     assert np.array_equal(second["rw"], ref2["rw"])
 
 
-@pytest.mark.parametrize("var", ["DSURF_EIKONAL_V1", "DSURF_EIKONAL_V2", "DSURF_EIKONAL_LAZY"])
+@pytest.mark.parametrize("var", ["DSURF_EIKONAL_V3", "DSURF_EIKONAL_V3,DSURF_EIKONAL_LAZY", "DSURF_MAXSLOTS=3,DSURF_MAXRAYS=20"])
 def test_reference_eikonal_variants_also_bit_exact(var):
-    """The simple (v1: one warp per sweep), overlapped (v2) and sub-warp (v3, default: 8 lanes per
-    sweep) marches must all reproduce the oracle; v1/v2 are selected by an environment variable at
-    process start."""
+    """The round-1 single-kernel march (16 lanes per sweep on (time, status) records, eager or lazy
+    back-pointers) must reproduce the oracle exactly like the default pipeline (k_refine +
+    lane-per-sweep k_march_lps); so must the default pipeline when sweeps are forced into several
+    batches, rays into several chunks, and the heap slab through its growth path.  Variants are
+    selected by environment variables at process start."""
     import os
     import subprocess
     import sys
 
     env = dict(os.environ)
-    env[var] = "1"
+    for kv in var.split(","):
+        k, _, v = kv.partition("=")
+        env[k] = v or "1"
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
                         "-k", "sweep_bit_exact or calsurfg_small"], env=env, capture_output=True, text=True)
