@@ -218,312 +218,331 @@ LPS_HD int sift_up(M &m, int tpc, float tv, int node, bool &moved) {
   return tpc;
 }
 
-// travel's march loop (:386-486) on the coarse grid (urg = 2 or 0: no refined-grid exit test).
+// Node ids are indices into the PADDED word array: node (ix, iz), 0-based, lives at
+// (ix + kPad) * ld + (iz + kPad) with ld = nnz + 2 * kPad; the kPad-wide frame is permanently far, so
+// stencil loads need no bounds tests (the reference's "outside the grid -> skip the side" tests
+// (:604-605) are evaluated on the coordinates).
+constexpr int kPad = 3;
+
+struct NbrOut {  // what the accepted node's neighbour g needs from the heap: nothing / addtree / updtree
+  int kind;      // 0: outside or alive, 1: far, 2: close
+  float tv;      // fouds2's trial time
+  uint32_t w;    // the neighbour's word as read (stored heap slot when close)
+};
+
+// fouds2 (:587-759) for neighbour g (0: ix-1, 1: ix+1, 2: iz-1, 3: iz+1) of the node `root` accepted
+// with key bits wX.  W: word(i), vel(i) on padded indices, risti(ix).
+template <class W>
+LPS_HD NbrOut eval_neighbour(const GridP &G, const W &wm, int root, uint32_t wX, int g) {
+  const int ld = G.nnz + 2 * kPad;
+  const int xp = root / ld;
+  const int ix = xp - kPad, iz = root - xp * ld - kPad;  // accepted node, 0-based
+  const int nx = ix + ((g == 0) ? -1 : (g == 1) ? 1 : 0), nz = iz + ((g == 2) ? -1 : (g == 3) ? 1 : 0);
+  const int nid = root + ((g == 0) ? -ld : (g == 1) ? ld : (g == 2) ? -1 : 1);
+  NbrOut o;
+  o.kind = 0;
+  o.tv = 0.0f;
+  o.w = kFar;
+  if (nx < 0 || nx >= G.nnx || nz < 0 || nz >= G.nnz) return o;
+  o.w = wm.word(nid);
+  if (alive(o.w)) return o;
+  o.kind = (o.w == kFar) ? 1 : 2;
+  uint32_t wj1[2], wj2[2], wk1[2], wk2[2];
+  bool inj[2], ink[2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int sd = 0; sd < 2; sd++) {
+    const int sg = sd ? 1 : -1;
+    inj[sd] = nx + sg >= 0 && nx + sg < G.nnx;
+    ink[sd] = nz + sg >= 0 && nz + sg < G.nnz;
+    // the accepted node is one of the 1-away nodes: it is alive with its key (its word may not be stored yet)
+    wj1[sd] = (nid + sg * ld == root) ? wX : wm.word(nid + sg * ld);
+    wj2[sd] = wm.word(nid + 2 * sg * ld);
+    wk1[sd] = (nid + sg == root) ? wX : wm.word(nid + sg);
+    wk2[sd] = wm.word(nid + 2 * sg);
+  }
+  o.tv = fouds2_words(wj1, wj2, inj, wk1, wk2, ink, 1.0f / wm.vel(nid), G.earth, wm.risti(nx), G.dnx, G.dnz);
+  return o;
+}
+
+// travel's march loop (:386-486) on the coarse grid (urg = 2 or 0: no refined-grid exit test): the HEAP side.
 // Returns 0 when the heap ran empty, -1 if the narrow band outgrew hcap, -2 on a broken invariant.
 //
-// M::kLanes lanes cooperate on one sweep (1 on the host, 4 on the device: lane g owns neighbour g of
-// the accepted node -- its stencil loads, its fouds2 and the prefetch of its heap chain); the heap
-// itself is walked redundantly by the lanes of a sweep (same addresses, same values).
+// The four fouds2 evaluations of an acceptance are independent of the heap (only alive nodes enter them)
+// and are obtained through the policy: m.publish(root, key, state) announces the accepted node,
+// m.collect(tv) returns the four trial times.  On the device they are computed by other warps of the block
+// (lane = sweep everywhere) while this warp sifts the heap; on the host collect() just calls eval_neighbour.
 //
 // Memory policy M:
-//   word(i) / set_word(i, w)   node words;  vel(i), risti(ix)   velocity and earth*sin(colatitude)
-//   hget(p) / hset(p, e)       heap slot p (1-based)
-//   hget2(p, a, b)             slots p (even) and p + 1
-//   hblock(q, e[14])           the 2 + 4 + 8 descendants of slot q at relative depths 1..3, q on a level
-//                              M::kLg - 1 + 3k (one 128-byte line of the device slab)
+//   word(i) / set_word(i, w)   node words (padded index)
+//   hget(p) / hset(p, e)       heap slot p (1-based);  hget2(p, a, b): slots p (even) and p + 1
+//   hblock(q, e[14], lim)      the 2 + 4 + 8 descendants of slot q at relative depths 1..3 (slots <= lim)
 //   M::kLg                     slots below 2^kLg are cheap (shared memory on the device)
-//   lane(), bcast(v, src), any(pred)   lane index inside the sweep's group, value of lane src, warp-wide OR
+//   div_ld(i)                  i / ld
+//   any(pred), sync()          warp-wide OR / re-convergence point;  publish / collect as above
 //
-// One acceptance is organised in dependent memory ROUND TRIPS:
-//   trip 1   stencil words + velocity of the owned neighbour(s), and the last heap element if it is not
-//            already in registers -- all issued together;
-//   trip 2-3 downtree: levels below 2^kLg from shared memory, then three levels per block fetch;
-//   trip 4   the ancestor chains of the (up to four) insert/update slots, fetched together; the
-//            updates are then applied in the reference's order from registers.  A three-entry log
-//            carries entries written by earlier neighbours of the same acceptance; a sift-up that
-//            moves entries (rare) sends the remaining neighbours to plain loads.
+// One acceptance is organised in dependent memory ROUND TRIPS (a warp is 32 unrelated sweeps and has the
+// scheduler almost to itself, so round trips and the length of the dependent instruction chain set the pace):
+//   trip 1   the four neighbour words and the last heap element (if it is not already in registers);
+//   trip 2-3 downtree: levels below 2^kLg from shared memory, then three levels per fetch;
+//   trip 4   the ancestor chains of the (up to four) insert/update slots, fetched together while the trial
+//            times are still being computed; the updates are then applied in the reference's order by
+//            straight-line code: three unrolled probes of the chain, the comparison with the parent, the
+//            write in place, and the patching of the later neighbours' prefetched copies.  Only an update
+//            that must MOVE entries (or whose entry sits higher than three levels above its stored slot)
+//            leaves this path for plain loops on memory, and sends the rest of the acceptance there too.
 template <class M>
 LPS_HD int march(const GridP &G, M &m, int ntr, int hcap) {
-  const int nnx = G.nnx, nnz = G.nnz;
-  constexpr int kSm = 1 << M::kLg;  // first slot outside the cheap levels
-  constexpr int kGC = 6;            // chain entries prefetched per neighbour (levels kLg .. kLg+5)
-  constexpr int NL = M::kLanes, NPER = 4 / NL;
-  const int me = m.lane();
+  const int ld = G.nnz + 2 * kPad;
+  constexpr int kGC = 4;  // chain entries prefetched per neighbour: three probes + the parent of the last
   Ent last;
   last.x = 0;
   last.y = -1;
   bool lastOK = false;
   int err = 0;
-  while (m.any(ntr > 0)) {  // the sweeps of a warp stay in lock step (all need ~nnx*nnz acceptances)
-    if (ntr <= 0) continue;
-    m.stat(2, ntr);
-    const Ent r = m.hget(1);
+  constexpr int kSm = 1 << M::kLg;  // first slot outside the cheap levels
+  for (;;) {  // the 32 sweeps of a warp stay in lock step (all need ~nnx*nnz acceptances)
+    const bool active = ntr > 0;
+    const bool anyact = m.any(active);
+    Ent r;
+    r.x = 0;
+    r.y = -1;
+    if (active) r = m.hget(1);
+    m.publish(r.y, (uint32_t)r.x, anyact ? (active ? 1 : 0) : -1);
+    if (!anyact) break;
     const int root = r.y;
-    const int ix = root / nnz, iz = root - ix * nnz;  // 0-based
-    const uint32_t wX = (uint32_t)r.x;                 // the accepted node: alive with its key
-    // ---- trip 1: the owned neighbour(s): own word, 8-point stencil (:620-663), velocity
-    uint32_t wN[NPER], wj1[NPER][2], wj2[NPER][2], wk1[NPER][2], wk2[NPER][2];
-    bool inN[NPER], inj[NPER][2], ink[NPER][2];
-    float vl[NPER];
-    auto ldw = [&](int x, int z) -> uint32_t {
-      if (x == ix && z == iz) return wX;
-      return (x >= 0 && x < nnx && z >= 0 && z < nnz) ? m.word(x * nnz + z) : kFar;
-    };
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int gi = 0; gi < NPER; gi++) {
-      const int g = me + NL * gi;
-      const int nx = ix + ((g == 0) ? -1 : (g == 1) ? 1 : 0), nz = iz + ((g == 2) ? -1 : (g == 3) ? 1 : 0);
-      inN[gi] = nx >= 0 && nx < nnx && nz >= 0 && nz < nnz;
-      wN[gi] = ldw(nx, nz);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int sd = 0; sd < 2; sd++) {
-        const int sg = sd ? 1 : -1;
-        inj[gi][sd] = nx + sg >= 0 && nx + sg < nnx;
-        ink[gi][sd] = nz + sg >= 0 && nz + sg < nnz;
-        wj1[gi][sd] = ldw(nx + sg, nz);
-        wj2[gi][sd] = ldw(nx + 2 * sg, nz);
-        wk1[gi][sd] = ldw(nx, nz + sg);
-        wk2[gi][sd] = ldw(nx, nz + 2 * sg);
-      }
-      vl[gi] = inN[gi] ? m.vel(nx * nnz + nz) : 1.0f;
-    }
-    if (!lastOK && ntr > 1) last = m.hget(ntr);
-    m.set_word(root, wX);  // alive, time = its key (:415-417)
-    // ---- trips 2-3: downtree (:816-885): the last element sinks from the root; entries pulled up are NOT recorded
-    int landed = -1;  // slot where the last element landed
-    if (ntr == 1) {
-      ntr = 0;
-    } else {
-      const float mk = bits2f(last.x);
-      ntr = ntr - 1;
-      int tpp = 1, tpc = 2;
-      bool stop = false;
-      while (!stop && tpc < ntr && tpc + 1 < kSm) {  // both children in the cheap levels
-        Ent e1, e2;
-        m.hget2(tpc, e1, e2);
-        Ent ec = e1;
-        if (bits2f(e1.x) > bits2f(e2.x)) {
-          tpc = tpc + 1;
-          ec = e2;
-        }
-        if (bits2f(ec.x) < mk) {
-          m.hset(tpp, ec);
-          tpp = tpc;
-          tpc = 2 * tpp;
-        } else {
-          stop = true;
-        }
-      }
-      while (!stop && tpc <= ntr) {
-        if (tpc + 1 < kSm) {  // single child inside the cheap levels (tpc == ntr)
-          const Ent ec = m.hget(tpc);
+    int kind[4] = {0, 0, 0, 0};  // 0: outside or alive, 1: far -> addtree, 2: close -> updtree
+    int q[4] = {0, 0, 0, 0};     // chain head: stored slot of a close node, parent of the new slot of a far node
+    Ent pre[4][kGC];
+    if (active) {
+      m.stat(2, ntr);
+      // ---- trip 1
+      uint32_t a1[4];
+      a1[0] = m.word(root - ld);
+      a1[1] = m.word(root + ld);
+      a1[2] = m.word(root - 1);
+      a1[3] = m.word(root + 1);
+      if (!lastOK && ntr > 1) last = m.hget(ntr);
+      m.set_word(root, (uint32_t)r.x);  // alive, time = its key (:415-417)
+      // ---- downtree (:816-885): the last element sinks from the root; entries pulled up are NOT recorded
+      int landed = -1;  // slot where the last element landed
+      if (ntr == 1) {
+        ntr = 0;
+      } else {
+        const float mk = bits2f(last.x);
+        ntr = ntr - 1;
+        int tpp = 1, tpc = 2;
+        bool stop = false;
+        while (!stop && tpc < ntr && tpc + 1 < kSm) {  // both children in the cheap levels
+          Ent e1, e2;
+          m.hget2(tpc, e1, e2);
+          Ent ec = e1;
+          if (bits2f(e1.x) > bits2f(e2.x)) {
+            tpc = tpc + 1;
+            ec = e2;
+          }
           if (bits2f(ec.x) < mk) {
             m.hset(tpp, ec);
             tpp = tpc;
+            tpc = 2 * tpp;
+          } else {
+            stop = true;
           }
-          break;
         }
-        Ent b[14];  // the three levels below tpp
-        m.hblock(tpp, b);
-        const int base = tpp;
-        int rel = 0;
+        while (!stop && tpc <= ntr) {
+          if (tpc + 1 < kSm) {  // single child inside the cheap levels (tpc == ntr)
+            const Ent ec = m.hget(tpc);
+            if (bits2f(ec.x) < mk) {
+              m.hset(tpp, ec);
+              tpp = tpc;
+            }
+            break;
+          }
+          Ent b[14];  // the three levels below tpp
+          m.hblock(tpp, b, ntr);
+          const int base = tpp;
+          int rel = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int lvl = 1; lvl <= 3; lvl++) {
-          const int c0 = (base << lvl) + 2 * rel;  // left child of the current slot
-          if (stop || c0 > ntr) {
-            stop = true;
-            continue;
+          for (int lvl = 1; lvl <= 3; lvl++) {
+            const int c0 = (base << lvl) + 2 * rel;  // left child of the current slot
+            if (stop || c0 > ntr) {
+              stop = true;
+              continue;
+            }
+            Ent e1, e2;
+            if (lvl == 1) {
+              e1 = b[0];
+              e2 = b[1];
+            } else if (lvl == 2) {
+              e1 = rel ? b[4] : b[2];
+              e2 = rel ? b[5] : b[3];
+            } else {
+              e1 = (rel == 0) ? b[6] : (rel == 1) ? b[8] : (rel == 2) ? b[10] : b[12];
+              e2 = (rel == 0) ? b[7] : (rel == 1) ? b[9] : (rel == 2) ? b[11] : b[13];
+            }
+            int pick = 0;
+            if (c0 < ntr && bits2f(e1.x) > bits2f(e2.x)) pick = 1;
+            const Ent ec = pick ? e2 : e1;
+            if (bits2f(ec.x) < mk) {
+              m.hset(tpp, ec);
+              tpp = c0 + pick;
+              rel = 2 * rel + pick;
+              if (c0 == ntr) stop = true;  // that was the single last child
+            } else {
+              stop = true;
+            }
           }
-          Ent e1, e2;
-          if (lvl == 1) {
-            e1 = b[0];
-            e2 = b[1];
-          } else if (lvl == 2) {
-            e1 = rel ? b[4] : b[2];
-            e2 = rel ? b[5] : b[3];
-          } else {
-            e1 = (rel == 0) ? b[6] : (rel == 1) ? b[8] : (rel == 2) ? b[10] : b[12];
-            e2 = (rel == 0) ? b[7] : (rel == 1) ? b[9] : (rel == 2) ? b[11] : b[13];
-          }
-          int pick = 0;
-          if (c0 < ntr && bits2f(e1.x) > bits2f(e2.x)) pick = 1;
-          const Ent ec = pick ? e2 : e1;
-          if (bits2f(ec.x) < mk) {
-            m.hset(tpp, ec);
-            tpp = c0 + pick;
-            rel = 2 * rel + pick;
-            if (c0 == ntr) stop = true;  // that was the single last child
-          } else {
-            stop = true;
-          }
+          tpc = 2 * tpp;
         }
-        tpc = 2 * tpp;
+        m.hset(tpp, last);
+        m.set_word(last.y, kCloseBit | (uint32_t)tpp);
+        landed = tpp;
       }
-      m.hset(tpp, last);
-      m.set_word(last.y, kCloseBit | (uint32_t)tpp);
-      landed = tpp;
-    }
-    lastOK = false;
-    // ---- trial times of the owned neighbour(s) (independent: only alive nodes enter fouds2)
-    float tvm[NPER];
-    int kindm[NPER];  // 0: nothing to do, 1: far -> addtree, 2: close -> updtree
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int gi = 0; gi < NPER; gi++) {
-      const int g = me + NL * gi;
-      kindm[gi] = 0;
-      tvm[gi] = 0.0f;
-      if (!inN[gi] || alive(wN[gi])) continue;
-      kindm[gi] = (wN[gi] == kFar) ? 1 : 2;
-      const int nix = ix + ((g == 0) ? -1 : (g == 1) ? 1 : 0);
-      tvm[gi] = fouds2_words(wj1[gi], wj2[gi], inj[gi], wk1[gi], wk2[gi], ink[gi], 1.0f / vl[gi], G.earth, m.risti(nix),
-                             G.dnx, G.dnz);
-    }
-    // ---- everybody learns the four results; chain heads
-    float tv[4];
-    int kind[4], q[4];  // q: first chain slot = stored slot of a close node, parent of the new slot of a far node
-    {
+      lastOK = false;
+      // ---- what the four neighbours need, and where their chains start
+      const int xp = m.div_ld(root), zp = root - xp * ld;
+      const bool inN[4] = {xp - 1 >= kPad, xp + 1 < G.nnx + kPad, zp - 1 >= kPad, zp + 1 < G.nnz + kPad};
       int nf = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
       for (int g = 0; g < 4; g++) {
-        kind[g] = m.bcast(kindm[g / NL], g % NL);
-        tv[g] = m.bcast(tvm[g / NL], g % NL);
-        uint32_t w = m.bcast(wN[g / NL], g % NL);
-        const int nidx = (g == 0) ? root - nnz : (g == 1) ? root + nnz : (g == 2) ? root - 1 : root + 1;
+        const int nidx = root + ((g == 0) ? -ld : (g == 1) ? ld : (g == 2) ? -1 : 1);
         // the words were read before downtree's store: the landed element may be this neighbour
-        if (kind[g] == 2 && landed >= 0 && last.y == nidx) w = kCloseBit | (uint32_t)landed;
-        q[g] = 0;
-        if (kind[g] == 1) {
-          nf++;
-          q[g] = (ntr + nf) >> 1;
-        } else if (kind[g] == 2) {
-          q[g] = (int)(w & 0x7FFFFFFFu);
+        if (landed >= 0 && last.y == nidx) a1[g] = kCloseBit | (uint32_t)landed;
+        if (inN[g] && !alive(a1[g])) {
+          if (a1[g] == kFar) {
+            kind[g] = 1;
+            nf++;
+            q[g] = (ntr + nf) >> 1;
+          } else {
+            kind[g] = 2;
+            q[g] = (int)(a1[g] & 0x7FFFFFFFu);
+          }
         }
       }
       if (ntr + nf > hcap) {
         err = -1;
         ntr = 0;
-        continue;
-      }
-    }
-    // ---- trip 4: chain slots of the owned heap operation(s), fetched together
-    Ent pre[NPER][kGC];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int gi = 0; gi < NPER; gi++) {
-      int q0 = q[0];
-      if (me + NL * gi == 1) q0 = q[1];
-      if (me + NL * gi == 2) q0 = q[2];
-      if (me + NL * gi == 3) q0 = q[3];
+        for (int g = 0; g < 4; g++) kind[g] = 0;
+      }
+      // ---- trip 4 (overlaps the computation of the trial times): the chains
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-      for (int c = 0; c < kGC; c++) {
-        const int sl = q0 >> c;
-        pre[gi][c].x = 0;
-        pre[gi][c].y = -1;
-        if (sl >= kSm && sl <= hcap) pre[gi][c] = m.hget(sl);
+      for (int g = 0; g < 4; g++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < kGC; c++) {
+          const int sl = q[g] >> c;
+          pre[g][c].x = 0;
+          pre[g][c].y = -1;
+          if (kind[g] != 0 && sl >= 1 && sl <= hcap) pre[g][c] = m.hget(sl);
+        }
       }
     }
-    // ---- apply in the reference's order x-1, x+1, z-1, z+1 (:419-440)
-    bool dirty = false;  // a sift-up of this acceptance moved entries: later neighbours read memory directly
-    int ls0 = -1, ls1 = -1, ls2 = -1, nl = 0;
-    Ent le0 = last, le1 = last, le2 = last;
+    // ---- the four trial times (computed elsewhere while the heap was sifted)
+    float tv[4];
+    m.collect(tv);
+    // ---- apply in the reference's order x-1, x+1, z-1, z+1 (:419-440).  Every lane walks the same four
+    // steps and re-converges (m.sync) before each: otherwise lanes whose neighbour needs nothing run ahead,
+    // the 32 sweeps drift apart and every path is replayed for 2-3 lanes at a time (profiles/r02_*).
+    bool dirty = false;  // an update of this acceptance took the slow path: the prefetched copies are stale
     int lastAt = -1;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int g = 0; g < 4; g++) {
-      if (kind[g] == 0) continue;
-      const int nidx = (g == 0) ? root - nnz : (g == 1) ? root + nnz : (g == 2) ? root - 1 : root + 1;
-      int q0 = q[g];
-      if (dirty && kind[g] == 2) q0 = (int)(m.word(nidx) & 0x7FFFFFFFu);
-      auto rd = [&](int sl, int c) -> Ent {  // chain reader: slot sl = q0 >> c
-        Ent e;
-        if (!dirty && sl >= kSm && c < kGC) {
-          Ent eo = pre[g / NL][0];  // select instead of indexing by c (registers)
-          if (c == 1) eo = pre[g / NL][1];
-          if (c == 2) eo = pre[g / NL][2];
-          if (c == 3) eo = pre[g / NL][3];
-          if (c == 4) eo = pre[g / NL][4];
-          if (c == 5) eo = pre[g / NL][5];
-          e.x = m.bcast(eo.x, g % NL);
-          e.y = m.bcast(eo.y, g % NL);
-        } else {
-          e = m.hget(sl);
+      m.sync();
+      if (kind[g] != 0 && err == 0) {
+        const int nidx = root + ((g == 0) ? -ld : (g == 1) ? ld : (g == 2) ? -1 : 1);
+        const float t = tv[g];
+        Ent ne;
+        ne.x = f2bits(t);
+        ne.y = nidx;
+        bool slow = dirty;
+        int p = 0, ps = 0;
+        Ent par = pre[g][0];
+        if (!slow) {
+          const int q0 = q[g];
+          if (kind[g] == 1) {
+            p = ntr + 1;
+            ps = q0;
+          } else {
+            m.stat(1, 1);
+            const bool m0 = q0 <= ntr && pre[g][0].y == nidx;
+            const bool m1 = (q0 >> 1) >= 1 && (q0 >> 1) <= ntr && pre[g][1].y == nidx;
+            const bool m2 = (q0 >> 2) >= 1 && (q0 >> 2) <= ntr && pre[g][2].y == nidx;
+            if (m0) {
+              p = q0;
+              par = pre[g][1];
+            } else if (m1) {
+              p = q0 >> 1;
+              par = pre[g][2];
+            } else if (m2) {
+              p = q0 >> 2;
+              par = pre[g][3];
+            } else {
+              slow = true;
+            }
+            ps = p >> 1;
+          }
+          if (!slow && ps >= 1 && t < bits2f(par.x)) slow = true;  // the entry has to move up
         }
-        if (!dirty) {  // entries written by earlier neighbours of this acceptance (none of them moved anything)
-          if (sl == ls0) e = le0;
-          if (sl == ls1) e = le1;
-          if (sl == ls2) e = le2;
-        }
-        return e;
-      };
-      int tpc, c = 0;
-      if (kind[g] == 1) {  // addtree (:768-805)
-        ntr = ntr + 1;
-        tpc = ntr;
-      } else {  // updtree (:894-921): locate the entry on the ancestor chain of the stored slot
-        int p = q0;
-        while (p > 0) {
-          m.stat(0, 1);
-          if (p <= ntr && rd(p, c).y == nidx) break;
-          p >>= 1;
-          c++;
-        }
-        m.stat(1, 1);
-        if (p == 0) {
-          err = -2;
-          break;
-        }
-        tpc = p;
-        c++;  // chain index of tpc's parent
-      }
-      const float t = tv[g];
-      bool moved = false;
-      int tpp = tpc >> 1;
-      while (tpp > 0) {
-        const Ent pe = rd(tpp, c);
-        if (t < bits2f(pe.x)) {
-          m.hset(tpc, pe);
-          m.set_word(pe.y, kCloseBit | (uint32_t)tpc);
-          tpc = tpp;
-          tpp = tpc >> 1;
-          c++;
-          moved = true;
-        } else {
-          tpp = 0;
-        }
-      }
-      Ent ne;
-      ne.x = f2bits(t);
-      ne.y = nidx;
-      m.hset(tpc, ne);
-      if (kind[g] == 1 || moved) m.set_word(nidx, kCloseBit | (uint32_t)tpc);
-      if (moved) {
-        dirty = true;
-        lastAt = -1;
-      } else {
-        if (nl == 0) { ls0 = tpc; le0 = ne; }
-        if (nl == 1) { ls1 = tpc; le1 = ne; }
-        if (nl == 2) { ls2 = tpc; le2 = ne; }
-        nl++;
-        if (kind[g] == 1 || tpc == lastAt) {  // the entry at the last slot is known
-          if (kind[g] == 1) lastAt = tpc;
-          last = ne;
+        if (!slow) {
+          if (kind[g] == 1) {
+            ntr = ntr + 1;
+            m.set_word(nidx, kCloseBit | (uint32_t)p);
+            last = ne;
+            lastAt = p;
+          } else if (p == lastAt) {
+            last = ne;
+          }
+          m.hset(p, ne);
+          // later neighbours of this acceptance may have this slot on their chains
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int g2 = g + 1; g2 < 4; g2++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int c2 = 0; c2 < kGC; c2++)
+              if ((q[g2] >> c2) == p) pre[g2][c2] = ne;
+          }
+        } else {  // plain loops on memory (every earlier write of this acceptance is there)
+          m.stat(3, 1);
+          dirty = true;
+          lastAt = -1;
+          int tpc;
+          if (kind[g] == 1) {  // addtree (:768-805)
+            ntr = ntr + 1;
+            tpc = ntr;
+          } else {  // updtree (:894-921): locate the entry on the ancestor chain of the stored slot
+            tpc = (int)(m.word(nidx) & 0x7FFFFFFFu);
+            while (tpc > 0) {
+              m.stat(0, 1);
+              if (tpc <= ntr && m.hget(tpc).y == nidx) break;
+              tpc >>= 1;
+            }
+            if (tpc == 0) err = -2;
+          }
+          if (tpc > 0) {
+            bool moved;
+            const int pos = sift_up(m, tpc, t, nidx, moved);
+            if (kind[g] == 1 || moved) m.set_word(nidx, kCloseBit | (uint32_t)pos);
+          }
         }
       }
     }
+    m.sync();
     if (err) ntr = 0;
     lastOK = (lastAt == ntr) && ntr > 0;
   }

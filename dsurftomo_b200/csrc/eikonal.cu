@@ -803,7 +803,8 @@ k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ 
   SweepDesc d = sw[slot];
   const size_t Nc = (size_t)g.nnx * g.nnz;
   const float *velv = velv_all + (size_t)d.map * g.nx * g.ny;
-  unsigned *word = bv.word + (size_t)slot * Nc;
+  const int wld = g.nnz + 2 * lps::kPad;  // padded word array (eik_lps.cuh)
+  unsigned *word = bv.word + (size_t)slot * ((size_t)(g.nnx + 2 * lps::kPad) * wld);
   int2 *noder = bv.noder + (size_t)slot * kRefMax * kRefMax;
   float *velr = bv.velr + (size_t)slot * kRefMax * kRefMax;
   int2 *box = bv.box + (size_t)slot * kBoxMax;
@@ -845,7 +846,7 @@ k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ 
       const int cz = base + gl;
       int2 v = make_int2(0, -1);
       if (cz < bh) v = box[cx * bh + cz];
-      const int xi = (d.vnl - 1 + cx) * g.nnz + (d.vnt - 1 + cz);
+      const int xi = (d.vnl - 1 + cx + lps::kPad) * wld + (d.vnt - 1 + cz + lps::kPad);  // padded node id
       const bool close = (v.y > 0 || v.y == -100);
       if (cz < bh && v.y == 0) word[xi] = (unsigned)v.x;
       const unsigned mask = (__ballot_sync(gm, close) >> gbase) & ((1u << kG) - 1u);
@@ -857,53 +858,31 @@ k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ 
 }
 
 constexpr int kLpsHS = 128;  // heap slots [1, 128) of every sweep live in shared memory, interleaved by sweep
+constexpr int kLpsNM = 2;    // fouds2 ("math") warps per group of 32 sweeps; each owns 4 / kLpsNM neighbours
+constexpr int kLpsThreads = 32 * (1 + kLpsNM);
+constexpr int kBarRoot = 1, kBarRes = 2;  // named barriers: accepted node published / trial times published
 
-// Heap slots >= kLpsHS live in a per-sweep global slab laid out in 128-byte blocks: block(q) holds
-// the 2 + 4 + 8 descendants of slot q at relative depths 1..3, for q on levels 6, 9, 12, ...  A
-// sift-down arriving at such a slot finds the next three levels in one line; the two children of a
-// slot are adjacent (one 16-byte load).
-__host__ __device__ __forceinline__ int lps_gaddr(int p) {
-#if defined(__CUDA_ARCH__)
-  const int lvl = 31 - __clz(p);
-#else
-  const int lvl = 31 - __builtin_clz((unsigned)p);
-#endif
-  const int gi = (lvl - 7) / 3, Lp = 6 + 3 * gi, d = lvl - Lp;
-  const int parent = p >> d;
-  const int blk = ((1 << Lp) - 64) / 7 + (parent - (1 << Lp));
-  return blk * 16 + (1 << d) - 2 + (p - (parent << d));
-}
-int lps_slab_entries(int hcap) {
-  if (hcap < kLpsHS) return 16;
-  const int lvl = 31 - __builtin_clz((unsigned)hcap);
-  const int gi = (lvl - 7) / 3, Lp = 6 + 3 * gi;
-  return (((1 << Lp) - 64) / 7 + (1 << Lp)) * 16;
-}
+// Heap slots >= kLpsHS live in a per-sweep global slab, slot p at entry p: the two children of a slot are one
+// aligned 16-byte pair, and the three levels below slot q are three contiguous runs (16, 32, 64 bytes).
+int lps_slab_entries(int hcap) { return (hcap + 8 + 15) & ~15; }  // whole 128-byte lines: every sweep's slab stays 16-byte aligned
 
-constexpr int kLpsLanes = 4;                   // lanes per sweep: lane g owns neighbour g of the accepted node
-constexpr int kLpsPerWarp = 32 / kLpsLanes;    // 8 sweeps per warp
-constexpr int kLpsWarps = 2;                   // warps per block
-
-struct LpsMem {
+// ---- policy of the heap warp (lane = sweep)
+struct LpsHeap {
   unsigned *w;
-  const float *v;
-  const float *ris;
-  int2 *sm;  // + sweep-in-warp; slot p at sm[p * kLpsPerWarp]: the 8 sweeps of a warp never share a bank pair
+  int2 *sm;   // + lane; slot p at sm[p * 32]
   int2 *gm;
-  unsigned gmask;  // the four lanes of this sweep
-  int gbase, me;
-  static constexpr int kLanes = kLpsLanes;
+  int2 *rootbuf;  // + lane
+  float *res;     // + lane; neighbour g at res[g * 32]
+  unsigned mdiv;  // i / ld == __umulhi(i, mdiv) >> sdiv (Grid::set_div)
+  int sdiv;
   static constexpr int kLg = 7;  // 2^7 = kLpsHS
-  __device__ __forceinline__ int lane() const { return me; }
-  template <class T>
-  __device__ __forceinline__ T bcast(T x, int src) const { return __shfl_sync(gmask, x, gbase + src); }
+  __device__ __forceinline__ int div_ld(int i) const { return (int)(__umulhi((unsigned)i, mdiv) >> sdiv); }
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(kFull, p); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ uint32_t word(int i) const { return w[i]; }
   __device__ __forceinline__ void set_word(int i, uint32_t x) const { w[i] = x; }
-  __device__ __forceinline__ float vel(int i) const { return __ldg(v + i); }
-  __device__ __forceinline__ float risti(int ix) const { return __ldg(ris + ix); }
   __device__ __forceinline__ lps::Ent hget(int p) const {
-    const int2 e = (p < kLpsHS) ? sm[p * kLpsPerWarp] : gm[lps_gaddr(p)];
+    const int2 e = (p < kLpsHS) ? sm[p * 32] : gm[p];
     lps::Ent r;
     r.x = e.x;
     r.y = e.y;
@@ -911,75 +890,136 @@ struct LpsMem {
   }
   __device__ __forceinline__ void hget2(int p, lps::Ent &a, lps::Ent &b) const {  // p even, both slots valid
     if (p < kLpsHS) {
-      const int2 e1 = sm[p * kLpsPerWarp], e2 = sm[(p + 1) * kLpsPerWarp];
+      const int2 e1 = sm[p * 32], e2 = sm[p * 32 + 32];
       a.x = e1.x; a.y = e1.y; b.x = e2.x; b.y = e2.y;
     } else {
-      const int4 e = *reinterpret_cast<const int4 *>(gm + lps_gaddr(p));
+      const int4 e = *reinterpret_cast<const int4 *>(gm + p);
       a.x = e.x; a.y = e.y; b.x = e.z; b.y = e.w;
     }
   }
   __device__ __forceinline__ void hset(int p, lps::Ent e) const {
     if (p < kLpsHS)
-      sm[p * kLpsPerWarp] = make_int2(e.x, e.y);
+      sm[p * 32] = make_int2(e.x, e.y);
     else
-      gm[lps_gaddr(p)] = make_int2(e.x, e.y);
+      gm[p] = make_int2(e.x, e.y);
   }
   __device__ __forceinline__ void stat(int, int) const {}
-  // block(q): the 14 descendants of slot q (q >= 64 on a level 6 + 3k) at relative depths 1..3 -- one 128-byte line
-  __device__ __forceinline__ void hblock(int q, lps::Ent b[14]) const {
-    const int Lp = 31 - __clz(q);
-    const int blk = ((1 << Lp) - 64) / 7 + (q - (1 << Lp));
-    const int4 *src = reinterpret_cast<const int4 *>(gm + (size_t)blk * 16);
+  // the 14 descendants of slot q (q >= 64) at relative depths 1..3; slots > lim are not read
+  __device__ __forceinline__ void hblock(int q, lps::Ent b[14], int lim) const {
+    int4 v[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) v[i] = make_int4(0, -1, 0, -1);
+    v[0] = *reinterpret_cast<const int4 *>(gm + 2 * q);
+    if (4 * q <= lim) {
+      v[1] = *reinterpret_cast<const int4 *>(gm + 4 * q);
+      v[2] = *reinterpret_cast<const int4 *>(gm + 4 * q + 2);
+    }
+    if (8 * q <= lim) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) v[3 + i] = *reinterpret_cast<const int4 *>(gm + 8 * q + 2 * i);
+    }
 #pragma unroll
     for (int i = 0; i < 7; i++) {
-      const int4 v = src[i];
-      b[2 * i].x = v.x; b[2 * i].y = v.y; b[2 * i + 1].x = v.z; b[2 * i + 1].y = v.w;
+      b[2 * i].x = v[i].x; b[2 * i].y = v[i].y; b[2 * i + 1].x = v[i].z; b[2 * i + 1].y = v[i].w;
     }
+  }
+  // state: 1 = this sweep accepted `root`, 0 = this sweep is finished, -1 = every sweep of the group is finished
+  __device__ __forceinline__ void publish(int root, uint32_t key, int state) const {
+    *rootbuf = make_int2(state == 1 ? root : (state == 0 ? -1 : -2), (int)key);
+    __threadfence_block();  // the node-word stores of the previous acceptance are visible to the math warps
+    __syncwarp();
+    asm volatile("bar.arrive %0, %1;" ::"r"(kBarRoot), "r"(kLpsThreads) : "memory");
+  }
+  __device__ __forceinline__ void collect(float tv[4]) const {
+    asm volatile("bar.sync %0, %1;" ::"r"(kBarRes), "r"(kLpsThreads) : "memory");
+#pragma unroll
+    for (int g = 0; g < 4; g++) tv[g] = res[g * 32];
   }
 };
-static_assert(kLpsHS == (1 << LpsMem::kLg), "shared-memory heap levels");
+static_assert(kLpsHS == (1 << LpsHeap::kLg), "shared-memory heap levels");
 
-__global__ void __launch_bounds__(kLpsWarps * 32)
+struct LpsWords {  // policy of the math warps
+  const unsigned *w;
+  const float *v;   // unpadded velocity map (iz fastest)
+  const float *ris;
+  int ld, nnz;
+  __device__ __forceinline__ uint32_t word(int i) const { return w[i]; }
+  __device__ __forceinline__ float vel(int i) const {  // padded id -> unpadded index
+    const int xp = i / ld;
+    return __ldg(v + (size_t)(xp - lps::kPad) * nnz + (i - xp * ld - lps::kPad));
+  }
+  __device__ __forceinline__ float risti(int ix) const { return __ldg(ris + ix); }
+};
+
+// One block = one group of 32 sweeps: warp 0 marches the 32 heaps (lane = sweep, lps::march), warps 1..kLpsNM
+// evaluate fouds2 for the neighbours of the 32 accepted nodes (lane = sweep as well) while the heaps are sifted.
+__global__ void __launch_bounds__(kLpsThreads, 6)
 k_march_lps(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
             const float *__restrict__ risti_c, BatchView bv) {
-  extern __shared__ int2 lsm[];
+  extern __shared__ int4 lsm4[];
+  int2 *heap = reinterpret_cast<int2 *>(lsm4);                       // [kLpsHS][32]
+  int2 *rootbuf = heap + kLpsHS * 32;                                // [32]
+  float *res = reinterpret_cast<float *>(rootbuf + 32);              // [4][32]
   const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = lane / kLpsLanes;
-  const int slot = (blockIdx.x * kLpsWarps + wp) * kLpsPerWarp + grp;
+  const int slot = blockIdx.x * 32 + lane;
   const bool valid = slot < nsw;
-  const size_t Nc = (size_t)g.nnx * g.nnz;
-  LpsMem m;
-  m.me = lane % kLpsLanes;
-  m.gbase = grp * kLpsLanes;
-  m.gmask = ((1u << kLpsLanes) - 1u) << m.gbase;
-  m.sm = lsm + (size_t)wp * kLpsHS * kLpsPerWarp + grp;
-  m.ris = risti_c;
-  m.w = nullptr;
-  m.v = nullptr;
-  m.gm = nullptr;
-  int ntr = 0;
-  if (valid) {
-    m.w = bv.word + (size_t)slot * Nc;
-    m.v = veln_all + (size_t)sw[slot].map * Nc;
-    m.gm = bv.hent + (size_t)slot * bv.slab;
-    const int ns = bv.nseed[slot];
-    const int2 *seed = bv.seed + (size_t)slot * kBoxMax;
-    for (int i = 0; i < ns; i++) {  // travel(urg=2)'s addtree scan (:341-347); the four lanes write the same values
-      const int2 s = seed[i];
-      bool moved;
-      ntr = ntr + 1;
-      const int pos = lps::sift_up(m, ntr, __int_as_float(s.x), s.y, moved);
-      m.set_word(s.y, lps::kCloseBit | (uint32_t)pos);
-    }
-  }
+  const int ld = g.nnz + 2 * lps::kPad;
+  const size_t Nw = (size_t)(g.nnx + 2 * lps::kPad) * ld;
   lps::GridP G;
   G.nnx = g.nnx;
   G.nnz = g.nnz;
   G.dnx = g.dnx;
   G.dnz = g.dnz;
   G.earth = g.earth;
-  const int rc = lps::march(G, m, ntr, bv.hcap);
-  if (valid && rc < 0 && m.me == 0) sw[slot].status = DSURF_ERR_HEAP;
+  if (wp == 0) {
+    LpsHeap m;
+    m.sm = heap + lane;
+    m.rootbuf = rootbuf + lane;
+    m.res = res + lane;
+    m.sdiv = 31 - __clz(ld);  // ld = nnz + 6 = 8k + 7 is never a power of two
+    m.mdiv = (unsigned)((1ull << (32 + m.sdiv)) / (unsigned)ld) + 1u;
+    m.w = nullptr;
+    m.gm = nullptr;
+    int ntr = 0;
+    if (valid) {
+      m.w = bv.word + (size_t)slot * Nw;
+      m.gm = bv.hent + (size_t)slot * bv.slab;
+      const int ns = bv.nseed[slot];
+      const int2 *seed = bv.seed + (size_t)slot * kBoxMax;
+      for (int i = 0; i < ns; i++) {  // travel(urg=2)'s addtree scan (:341-347)
+        const int2 s = seed[i];
+        bool moved;
+        ntr = ntr + 1;
+        const int pos = lps::sift_up(m, ntr, __int_as_float(s.x), s.y, moved);
+        m.set_word(s.y, lps::kCloseBit | (uint32_t)pos);
+      }
+    }
+    const int rc = lps::march(G, m, ntr, bv.hcap);
+    if (valid && rc < 0) sw[slot].status = DSURF_ERR_HEAP;
+  } else {
+    LpsWords wm;
+    wm.w = valid ? bv.word + (size_t)slot * Nw : nullptr;
+    wm.v = valid ? veln_all + (size_t)sw[slot].map * ((size_t)g.nnx * g.nnz) : nullptr;
+    wm.ris = risti_c;
+    wm.ld = ld;
+    wm.nnz = g.nnz;
+    constexpr int kPer = 4 / kLpsNM;
+    for (;;) {
+      asm volatile("bar.sync %0, %1;" ::"r"(kBarRoot), "r"(kLpsThreads) : "memory");
+      const int2 rb = rootbuf[lane];
+      if (rb.x == -2) break;  // uniform: the heap warp publishes -2 to every lane at once
+#pragma unroll
+      for (int k = 0; k < kPer; k++) {
+        const int gq = (wp - 1) * kPer + k;
+        float tv = 0.0f;
+        if (rb.x >= 0) tv = lps::eval_neighbour(G, wm, rb.x, (uint32_t)rb.y, gq).tv;
+        __syncwarp();
+        res[gq * 32 + lane] = tv;
+      }
+      __syncwarp();
+      asm volatile("bar.arrive %0, %1;" ::"r"(kBarRes), "r"(kLpsThreads) : "memory");
+    }
+  }
 }
 
 static bool legacy_v3() {
@@ -1008,6 +1048,7 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
                    const float *d_velv_all, const float *d_risti, BatchView bv, int *launches) {
   if (nsw <= 0) return DSURF_OK;
   const long long ntot = (long long)nsw * g.nnx * g.nnz;
+  const long long nwtot = (long long)nsw * (g.nnx + 2 * lps::kPad) * (g.nnz + 2 * lps::kPad);
   SweepDesc *sw = const_cast<SweepDesc *>(d_sw);
   const int nt = kWarpsPerBlock * 32;
   const int per_block = kWarpsPerBlock * V3<16>::NG;
@@ -1019,6 +1060,7 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DS_CUDA(cudaFuncSetAttribute(k_refine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DS_CUDA(cudaFuncSetAttribute(k_march_lps, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DS_CUDA(cudaFuncSetAttribute(k_march_lps, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
     attr = true;
   }
   if (legacy_v3()) {
@@ -1032,12 +1074,11 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     if (launches) *launches += 2;
     return DSURF_OK;
   }
-  DS_CUDA(cudaMemsetAsync(bv.word, 0xFF, (size_t)ntot * sizeof(unsigned), st));  // every node far
+  DS_CUDA(cudaMemsetAsync(bv.word, 0xFF, (size_t)nwtot * sizeof(unsigned), st));  // every node (and the frame) far
   k_refine<16><<<grid3, nt, smem, st>>>(g, sw, nsw, d_velv_all, bv);
   DS_CUDA(cudaGetLastError());
-  const int per_blk = kLpsWarps * kLpsPerWarp;
-  k_march_lps<<<(nsw + per_blk - 1) / per_blk, kLpsWarps * 32, (size_t)kLpsWarps * kLpsHS * kLpsPerWarp * sizeof(int2), st>>>(
-      g, sw, nsw, d_veln_all, d_risti, bv);
+  const size_t lsm = (size_t)kLpsHS * 32 * sizeof(int2) + 32 * sizeof(int2) + 4 * 32 * sizeof(float);
+  k_march_lps<<<(nsw + 31) / 32, kLpsThreads, lsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv);
   DS_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   return DSURF_OK;

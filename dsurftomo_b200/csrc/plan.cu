@@ -348,7 +348,8 @@ static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const floa
   p->words = eikonal_uses_words();
   const size_t slab = (size_t)eikonal_slab_entries(p->hcap);
   const size_t kBox = (size_t)(2 * kSgs + 1) * (2 * kSgs + 1);
-  const size_t per_slot = Nc * (p->words ? sizeof(unsigned) : sizeof(int2)) +
+  const size_t Nw = (size_t)(p->g.nnx + 6) * (p->g.nnz + 6);  // padded word array of the round-2 march (eik_lps.cuh, kPad = 3)
+  const size_t per_slot = (p->words ? Nw * sizeof(unsigned) : Nc * sizeof(int2)) +
                           (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) + slab * sizeof(int2) +
                           kRefMax * sizeof(float) + sizeof(SweepDesc) + kBox * 2 * sizeof(int2) + sizeof(int);
   // rays are traced and assembled in chunks of at most maxrays (their dense fdm slabs dominate otherwise)
@@ -379,7 +380,7 @@ static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const floa
   p->maxslots = (int)ms;
   bad = false;
   if (p->words) {
-    bad |= p->word.reserve((size_t)p->maxslots * Nc) != cudaSuccess;
+    bad |= p->word.reserve((size_t)p->maxslots * Nw) != cudaSuccess;
     bad |= p->box.reserve((size_t)p->maxslots * kBox) != cudaSuccess;
     bad |= p->seed.reserve((size_t)p->maxslots * kBox) != cudaSuccess;
     bad |= p->nseed.reserve((size_t)p->maxslots) != cudaSuccess;
@@ -883,8 +884,10 @@ extern "C" int dsurf_plan_debug_sweep(dsurf_plan *p, int gidx, int ig, float *ve
   const size_t Nc = (size_t)g.nnx * g.nnz;
   const SweepDesc &d = hsw[0];
   if (veln) DS_CUDA(cudaMemcpy(veln, p->veln_all.p + (size_t)d.map * Nc, Nc * sizeof(float), cudaMemcpyDeviceToHost));
-  if (ttn && p->words) {
-    DS_CUDA(cudaMemcpy(ttn, p->word.p, Nc * sizeof(float), cudaMemcpyDeviceToHost));  // every node alive: word = time
+  if (ttn && p->words) {  // every node alive: word = time; strip the 3-node frame
+    const size_t wld = (size_t)g.nnz + 6;
+    DS_CUDA(cudaMemcpy2D(ttn, g.nnz * sizeof(float), p->word.p + 3 * wld + 3, wld * sizeof(float), g.nnz * sizeof(float),
+                         g.nnx, cudaMemcpyDeviceToHost));
   } else if (ttn) {
     std::vector<int2> tmp(Nc);
     DS_CUDA(cudaMemcpy(tmp.data(), p->node.p, Nc * sizeof(int2), cudaMemcpyDeviceToHost));

@@ -15,19 +15,23 @@
 using namespace dsurf::lps;
 
 struct HostMem {
-  std::vector<uint32_t> w;
-  const float *v;
+  GridP G;
+  std::vector<uint32_t> w;  // padded (nnx + 6) x (nnz + 6), frame = far
+  std::vector<float> v;     // same padded indexing
   std::vector<float> ris;
   std::vector<Ent> h;
-  long long probes = 0, lookups = 0, wstores = 0, pops = 0, ntr_sum = 0;
+  long long probes = 0, lookups = 0, wstores = 0, pops = 0, ntr_sum = 0, slow = 0;
   int ntr_max = 0;
-  void stat(int k, int v) {
-    if (k == 0) probes += v;
-    if (k == 1) lookups += v;
+  int pub_root = -1, pub_state = 0;
+  uint32_t pub_key = 0;
+  void stat(int k, int v_) {
+    if (k == 0) probes += v_;
+    if (k == 1) lookups += v_;
+    if (k == 3) slow += v_;
     if (k == 2) {
       pops++;
-      ntr_sum += v;
-      if (v > ntr_max) ntr_max = v;
+      ntr_sum += v_;
+      if (v_ > ntr_max) ntr_max = v_;
     }
   }
   uint32_t word(int i) const { return w[i]; }
@@ -37,25 +41,33 @@ struct HostMem {
   }
   float vel(int i) const { return v[i]; }
   float risti(int ix) const { return ris[ix]; }
-  Ent hget(int p) {
-    return h[p];
-  }
+  Ent hget(int p) { return h[p]; }
   void hget2(int p, Ent &a, Ent &b) {
     a = h[p];
     b = h[p + 1];
   }
   void hset(int p, Ent e) { h[p] = e; }
-  static constexpr int kLanes = 1;
-  int lane() const { return 0; }
-  template <class T> T bcast(T v, int) const { return v; }
   bool any(bool p) const { return p; }
+  void sync() const {}
+  void publish(int root, uint32_t key, int state) {
+    pub_root = root;
+    pub_key = key;
+    pub_state = state;
+  }
+  void collect(float tv[4]) {  // on the device other warps do this while the heap is sifted
+    for (int g = 0; g < 4; g++) {
+      tv[g] = 0.0f;
+      if (pub_state == 1) tv[g] = eval_neighbour(G, *this, pub_root, pub_key, g).tv;
+    }
+  }
+  int div_ld(int i) const { return i / (G.nnz + 2 * kPad); }
   static constexpr int kLg = LPS_HOST_KLG;  // cheap levels of the device layout (7 there); small values exercise the block walk
-  void hblock(int q, Ent b[14]) {
+  void hblock(int q, Ent b[14], int lim) {
     int k = 0;
     for (int d = 1; d <= 3; d++)
       for (int o = 0; o < (1 << d); o++) {
         const size_t sl = ((size_t)q << d) + o;
-        b[k++] = sl < h.size() ? h[sl] : Ent{0, -1};
+        b[k++] = (sl <= (size_t)lim) ? h[sl] : Ent{0, -1};
       }
   }
 };
@@ -82,11 +94,12 @@ static int run_case(int nx, int ny, unsigned seed, int kind, float fx, float fz)
   if (isx == nnx) isx--;
   if (isz == nnz) isz--;
   HostMem m;
-  m.w.assign((size_t)nnx * nnz, kFar);
-  std::vector<float> vel((size_t)nnx * nnz);
+  const int ld = nnz + 2 * kPad;
+  m.G = GridP{nnx, nnz, f.dnx, f.dnz, f.earth};
+  m.w.assign((size_t)(nnx + 2 * kPad) * ld, kFar);
+  m.v.assign(m.w.size(), 1.0f);
   for (int ix = 1; ix <= nnx; ix++)
-    for (int iz = 1; iz <= nnz; iz++) vel[(size_t)(ix - 1) * nnz + (iz - 1)] = f.V(iz, ix);
-  m.v = vel.data();
+    for (int iz = 1; iz <= nnz; iz++) m.v[(size_t)(ix - 1 + kPad) * ld + (iz - 1 + kPad)] = f.V(iz, ix);
   m.ris.resize(nnx);
   for (int ix = 1; ix <= nnx; ix++) m.ris[ix - 1] = f.earth * std::sin(f.gox + (float)(ix - 1) * f.dnx);
   const int hcap = nnx * nnz / 2 + 8;
@@ -102,14 +115,13 @@ static int run_case(int nx, int ny, unsigned seed, int kind, float fx, float fz)
       const float ex = dsx - (float)(i - 1) * f.dnx, ez = dsz - (float)(j - 1) * f.dnz;
       const float ds = std::sqrt(ex * ex + ez * ez);
       const float t0 = 2.0f * ds / (vss[i][j] + vsrc);
-      const int nid = (isx - 1 + i - 1) * nnz + (isz - 1 + j - 1);
+      const int nid = (isx - 1 + i - 1 + kPad) * ld + (isz - 1 + j - 1 + kPad);
       bool moved;
       ntr++;
       const int pos = sift_up(m, ntr, t0, nid, moved);
       m.set_word(nid, kCloseBit | (uint32_t)pos);
     }
-  GridP G{nnx, nnz, f.dnx, f.dnz, f.earth};
-  const int rc = march(G, m, ntr, hcap);
+  const int rc = march(m.G, m, ntr, hcap);
   f.travel(scx, scz, 0);
   if (rc != 0 || f.error) {
     printf("FAIL rc=%d err=%d\n", rc, f.error);
@@ -121,12 +133,12 @@ static int run_case(int nx, int ny, unsigned seed, int kind, float fx, float fz)
       const float t = f.T(iz, ix);
       uint32_t b;
       memcpy(&b, &t, 4);
-      if (b != m.w[(size_t)(ix - 1) * nnz + (iz - 1)]) bad++;
+      if (b != m.w[(size_t)(ix - 1 + kPad) * ld + (iz - 1 + kPad)]) bad++;
     }
   printf("case nx=%d ny=%d kind=%d src=(%.2f,%.2f): %dx%d nodes, mismatches=%lld, word stores/pop=%.2f, "
-         "lookups/pop=%.2f probes/lookup=%.2f heap mean=%.0f max=%d\n", nx, ny, kind, fx, fz, nnx, nnz, bad,
+         "lookups/pop=%.2f slow-path updates/pop=%.3f heap mean=%.0f max=%d\n", nx, ny, kind, fx, fz, nnx, nnz, bad,
          (double)m.wstores / (double)m.pops, (double)m.lookups / (double)m.pops,
-         (double)m.probes / (double)(m.lookups ? m.lookups : 1), (double)m.ntr_sum / (double)m.pops, m.ntr_max);
+         (double)m.slow / (double)m.pops, (double)m.ntr_sum / (double)m.pops, m.ntr_max);
   return bad != 0;
 }
 
