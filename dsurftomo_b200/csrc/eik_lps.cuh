@@ -282,20 +282,21 @@ LPS_HD NbrOut eval_neighbour(const GridP &G, const W &wm, int root, uint32_t wX,
 //   div_ld(i)                  i / ld
 //   any(pred), sync()          warp-wide OR / re-convergence point;  publish / collect as above
 //
-// One acceptance is organised in dependent memory ROUND TRIPS (a warp is 32 unrelated sweeps and has the
-// scheduler almost to itself, so round trips and the length of the dependent instruction chain set the pace):
-//   trip 1   the four neighbour words and the last heap element (if it is not already in registers);
+// One acceptance is organised in a FIXED schedule of dependent memory round trips.  A warp is 32 unrelated
+// sweeps that advance in lock step, so the slowest lane sets the pace of every acceptance: no lane may take a
+// private detour through memory, however rare (measured: with 32 lanes a 5 % event happens every time).
+//   trip 1   the four neighbour words (decides addtree / updtree / nothing and gives the stored slots);
 //   trip 2-3 downtree: levels below 2^kLg from shared memory, then three levels per fetch;
-//   trip 4   the ancestor chains of the (up to four) insert/update slots, fetched together while the trial
-//            times are still being computed; the updates are then applied in the reference's order by
-//            straight-line code: three unrolled probes of the chain, the comparison with the parent, the
-//            write in place, and the patching of the later neighbours' prefetched copies.  Only an update
-//            that must MOVE entries (or whose entry sits higher than three levels above its stored slot)
-//            leaves this path for plain loops on memory, and sends the rest of the acceptance there too.
+//   trip 4   issued while the trial times are still being computed: for each of the (up to four) heap
+//            operations EVERY chain slot outside the cheap levels, plus the heap's last slot.
+// The updates are then applied in the reference's order from registers and shared memory only: every heap
+// write goes through put(), which also patches the later neighbours' prefetched copies and the tracked last
+// element (the next downtree starts from it without a load).  The one case that re-reads memory is a later
+// neighbour being pushed down by an earlier neighbour's sift-up (its chain changes altogether).
 template <class M>
 LPS_HD int march(const GridP &G, M &m, int ntr, int hcap) {
   const int ld = G.nnz + 2 * kPad;
-  constexpr int kGC = 4;  // chain entries prefetched per neighbour: three probes + the parent of the last
+  constexpr int kGC = 6;  // prefetched chain entries per neighbour: every level outside the cheap ones up to slot 2^(kLg+6) - 1
   Ent last;
   last.x = 0;
   last.y = -1;
@@ -323,7 +324,7 @@ LPS_HD int march(const GridP &G, M &m, int ntr, int hcap) {
       a1[1] = m.word(root + ld);
       a1[2] = m.word(root - 1);
       a1[3] = m.word(root + 1);
-      if (!lastOK && ntr > 1) last = m.hget(ntr);
+      if (!lastOK && ntr > 1) last = m.hget(ntr);  // first acceptance only: afterwards the last element is tracked
       m.set_word(root, (uint32_t)r.x);  // alive, time = its key (:415-417)
       // ---- downtree (:816-885): the last element sinks from the root; entries pulled up are NOT recorded
       int landed = -1;  // slot where the last element landed
@@ -432,7 +433,7 @@ LPS_HD int march(const GridP &G, M &m, int ntr, int hcap) {
 #endif
         for (int g = 0; g < 4; g++) kind[g] = 0;
       }
-      // ---- trip 4 (overlaps the computation of the trial times): the chains
+      // ---- trip 4 (overlaps the computation of the trial times): the chains and the last slot
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -444,9 +445,10 @@ LPS_HD int march(const GridP &G, M &m, int ntr, int hcap) {
           const int sl = q[g] >> c;
           pre[g][c].x = 0;
           pre[g][c].y = -1;
-          if (kind[g] != 0 && sl >= 1 && sl <= hcap) pre[g][c] = m.hget(sl);
+          if (kind[g] != 0 && sl >= kSm && sl <= hcap) pre[g][c] = m.hget(sl);
         }
       }
+      if (ntr >= 1) last = m.hget(ntr);
     }
     // ---- the four trial times (computed elsewhere while the heap was sifted)
     float tv[4];
@@ -454,8 +456,7 @@ LPS_HD int march(const GridP &G, M &m, int ntr, int hcap) {
     // ---- apply in the reference's order x-1, x+1, z-1, z+1 (:419-440).  Every lane walks the same four
     // steps and re-converges (m.sync) before each: otherwise lanes whose neighbour needs nothing run ahead,
     // the 32 sweeps drift apart and every path is replayed for 2-3 lanes at a time (profiles/r02_*).
-    bool dirty = false;  // an update of this acceptance took the slow path: the prefetched copies are stale
-    int lastAt = -1;
+    bool refresh[4] = {false, false, false, false};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -463,88 +464,98 @@ LPS_HD int march(const GridP &G, M &m, int ntr, int hcap) {
       m.sync();
       if (kind[g] != 0 && err == 0) {
         const int nidx = root + ((g == 0) ? -ld : (g == 1) ? ld : (g == 2) ? -1 : 1);
-        const float t = tv[g];
-        Ent ne;
-        ne.x = f2bits(t);
-        ne.y = nidx;
-        bool slow = dirty;
-        int p = 0, ps = 0;
-        Ent par = pre[g][0];
-        if (!slow) {
-          const int q0 = q[g];
-          if (kind[g] == 1) {
-            p = ntr + 1;
-            ps = q0;
-          } else {
-            m.stat(1, 1);
-            const bool m0 = q0 <= ntr && pre[g][0].y == nidx;
-            const bool m1 = (q0 >> 1) >= 1 && (q0 >> 1) <= ntr && pre[g][1].y == nidx;
-            const bool m2 = (q0 >> 2) >= 1 && (q0 >> 2) <= ntr && pre[g][2].y == nidx;
-            if (m0) {
-              p = q0;
-              par = pre[g][1];
-            } else if (m1) {
-              p = q0 >> 1;
-              par = pre[g][2];
-            } else if (m2) {
-              p = q0 >> 2;
-              par = pre[g][3];
-            } else {
-              slow = true;
-            }
-            ps = p >> 1;
+        if (refresh[g]) {  // an earlier sift-up pushed this neighbour down to slot q[g]: its chain is new
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+          for (int c = 0; c < kGC; c++) {
+            const int sl = q[g] >> c;
+            if (sl >= kSm && sl <= hcap) pre[g][c] = m.hget(sl);
           }
-          if (!slow && ps >= 1 && t < bits2f(par.x)) slow = true;  // the entry has to move up
         }
-        if (!slow) {
-          if (kind[g] == 1) {
-            ntr = ntr + 1;
-            m.set_word(nidx, kCloseBit | (uint32_t)p);
-            last = ne;
-            lastAt = p;
-          } else if (p == lastAt) {
-            last = ne;
-          }
-          m.hset(p, ne);
-          // later neighbours of this acceptance may have this slot on their chains
+        auto ent_at = [&](int sl, int c) -> Ent {  // chain slot sl = q[g] >> c
+          if (sl < kSm || c >= kGC) return m.hget(sl);
+          Ent e = pre[g][0];  // g is a compile-time constant after unrolling; select instead of indexing by c
+          if (c == 1) e = pre[g][1];
+          if (c == 2) e = pre[g][2];
+          if (c == 3) e = pre[g][3];
+          if (c == 4) e = pre[g][4];
+          if (c == 5) e = pre[g][5];
+          return e;
+        };
+        auto put = [&](int sl, Ent e) {  // every heap write of the apply phase
+          m.hset(sl, e);
+          if (sl == ntr) last = e;
+          if (sl >= kSm) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-          for (int g2 = g + 1; g2 < 4; g2++) {
+            for (int g2 = g + 1; g2 < 4; g2++) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int c2 = 0; c2 < kGC; c2++)
-              if ((q[g2] >> c2) == p) pre[g2][c2] = ne;
-          }
-        } else {  // plain loops on memory (every earlier write of this acceptance is there)
-          m.stat(3, 1);
-          dirty = true;
-          lastAt = -1;
-          int tpc;
-          if (kind[g] == 1) {  // addtree (:768-805)
-            ntr = ntr + 1;
-            tpc = ntr;
-          } else {  // updtree (:894-921): locate the entry on the ancestor chain of the stored slot
-            tpc = (int)(m.word(nidx) & 0x7FFFFFFFu);
-            while (tpc > 0) {
-              m.stat(0, 1);
-              if (tpc <= ntr && m.hget(tpc).y == nidx) break;
-              tpc >>= 1;
+              for (int c2 = 0; c2 < kGC; c2++)
+                if ((q[g2] >> c2) == sl) pre[g2][c2] = e;
             }
-            if (tpc == 0) err = -2;
           }
-          if (tpc > 0) {
-            bool moved;
-            const int pos = sift_up(m, tpc, t, nidx, moved);
-            if (kind[g] == 1 || moved) m.set_word(nidx, kCloseBit | (uint32_t)pos);
+        };
+        int tpc, c;  // slot of the entry and chain index of its parent
+        if (kind[g] == 1) {  // addtree (:768-805)
+          ntr = ntr + 1;
+          tpc = ntr;
+          c = 0;
+        } else {  // updtree (:894-921): locate the entry on the ancestor chain of the stored slot
+          m.stat(1, 1);
+          tpc = q[g];
+          c = 0;
+          while (tpc > 0) {
+            m.stat(0, 1);
+            if (tpc <= ntr && ent_at(tpc, c).y == nidx) break;
+            tpc >>= 1;
+            c++;
           }
+          if (tpc == 0) err = -2;
+          c++;
+        }
+        if (tpc > 0) {
+          const float t = tv[g];
+          bool moved = false;
+          int tpp = tpc >> 1;
+          while (tpp > 0) {
+            const Ent pe = ent_at(tpp, c);
+            if (t < bits2f(pe.x)) {
+              put(tpc, pe);
+              m.set_word(pe.y, kCloseBit | (uint32_t)tpc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+              for (int g2 = g + 1; g2 < 4; g2++) {  // a later neighbour pushed down: its exact slot is tpc now
+                const int n2 = root + ((g2 == 0) ? -ld : (g2 == 1) ? ld : (g2 == 2) ? -1 : 1);
+                if (kind[g2] == 2 && pe.y == n2) {
+                  q[g2] = tpc;
+                  refresh[g2] = true;
+                }
+              }
+              tpc = tpp;
+              tpp = tpc >> 1;
+              c++;
+              moved = true;
+            } else {
+              tpp = 0;
+            }
+          }
+          Ent ne;
+          ne.x = f2bits(t);
+          ne.y = nidx;
+          put(tpc, ne);
+          if (kind[g] == 1 || moved) m.set_word(nidx, kCloseBit | (uint32_t)tpc);
+          if (moved) m.stat(3, 1);
         }
       }
     }
     m.sync();
     if (err) ntr = 0;
-    lastOK = (lastAt == ntr) && ntr > 0;
+    lastOK = ntr > 0;
   }
   return err;
 }

@@ -1022,8 +1022,14 @@ k_march_lps(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict
   }
 }
 
+// Pipeline selection.  Default: the single-kernel march with 16 lanes per sweep (k_eikonal3).  DSURF_EIKONAL_LPS=1
+// selects k_refine + k_march_lps (lane per sweep, warp-specialised).  Measured on B200 at cfg 3 (profiles/
+// r02_eikonal_lps.md): 33 s per stage against 22.6 s -- with one lane per sweep every load touches 32 distinct lines
+// and the slowest of 32 unrelated sweeps sets the pace of each acceptance, so the time per acceptance grows from
+// 8.6 us (1 K sweeps resident) to 27.5 us (24.6 K); it needs 2.4x fewer DRAM bytes and 5x fewer issue slots per
+// accepted node, but the machine is latency-, not throughput-bound on this path.
 static bool legacy_v3() {
-  static const bool v = getenv("DSURF_EIKONAL_V3") != nullptr;
+  static const bool v = getenv("DSURF_EIKONAL_LPS") == nullptr;
   return v;
 }
 bool eikonal_uses_words() { return !legacy_v3(); }

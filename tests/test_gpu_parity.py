@@ -325,13 +325,14 @@ def test_device_glue_matches_host_glue(taipei):
     assert np.array_equal(second["rw"], ref2["rw"])
 
 
-@pytest.mark.parametrize("var", ["DSURF_EIKONAL_V3", "DSURF_EIKONAL_V3,DSURF_EIKONAL_LAZY", "DSURF_MAXSLOTS=3,DSURF_MAXRAYS=20"])
+@pytest.mark.parametrize("var", ["DSURF_EIKONAL_LPS", "DSURF_EIKONAL_LAZY", "DSURF_MAXSLOTS=3,DSURF_MAXRAYS=20",
+                                 "DSURF_EIKONAL_LPS,DSURF_MAXSLOTS=40,DSURF_MAXRAYS=20", "DSURF_EIKONAL_LPS,DSURF_HCAP=600"])
 def test_reference_eikonal_variants_also_bit_exact(var):
-    """The round-1 single-kernel march (16 lanes per sweep on (time, status) records, eager or lazy
-    back-pointers) must reproduce the oracle exactly like the default pipeline (k_refine +
-    lane-per-sweep k_march_lps); so must the default pipeline when sweeps are forced into several
-    batches, rays into several chunks, and the heap slab through its growth path.  Variants are
-    selected by environment variables at process start."""
+    """The lane-per-sweep pipeline (k_refine + warp-specialised k_march_lps on one word per node with
+    lazy heap back-pointers, DSURF_EIKONAL_LPS) and the lazy-back-pointer variant of the default
+    16-lanes-per-sweep march must reproduce the oracle exactly like the default; so must both
+    pipelines when sweeps are forced into several batches, rays into several chunks, and the heap
+    slab through its growth path.  Variants are selected by environment variables at process start."""
     import os
     import subprocess
     import sys
@@ -342,7 +343,7 @@ def test_reference_eikonal_variants_also_bit_exact(var):
         env[k] = v or "1"
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
-                        "-k", "sweep_bit_exact or calsurfg_small"], env=env, capture_output=True, text=True)
+                        "-k", "sweep_bit_exact or calsurfg_small or full_size_grid"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
