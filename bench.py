@@ -118,9 +118,24 @@ def lsmr_bytes(nnz, m, n):
     return 16 * nnz + 8 * (m + 1) + 12 * m + 80 * n
 
 
+def make_config(pb, world, step_mode):
+    """The `config` object of the JSON line -- identical keys and values in both arms."""
+    return dict(workload=pb.name, grid=f"{(pb.nx - 3) * 8 + 1}x{(pb.ny - 3) * 8 + 1}",
+                step=("one full CalSurfG sweep stage: every (period, type, source) gather of the workload, "
+                      "sharded over the GPUs in contiguous gather blocks" if step_mode == "stage" else
+                      "all periods x sources of one data type per step (A/B runs only)"),
+                sweeps_per_step=int(pb.nsrc1[: pb.kmaxRc].sum() + 2 * pb.nsrc1[pb.kmaxRc: pb.kmaxRc + pb.kmaxRg].sum() +
+                                    pb.nsrc1[pb.kmaxRc + pb.kmaxRg: pb.kmaxRc + pb.kmaxRg + pb.kmaxLc].sum() +
+                                    2 * pb.nsrc1[pb.kmaxRc + pb.kmaxRg + pb.kmaxLc:].sum()),
+                receivers_per_gather=int(pb.nrc1.max()),
+                l2="per-step working set (node states of thousands of sweeps, tens of GB) >> 126 MB L2",
+                interpretation="A: quoted grid = FMM propagation grid (SURVEY.md section 8)")
+
+
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, step, nthreads):
-    """Oracle sweep stage on `per_block` gathers of every data-type block; returns (sweeps, s)."""
+def cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, step, nthreads, mode=1):
+    """Oracle sweep stage on `per_block` gathers of every data-type block; returns (sweeps, s).
+    mode 1: independent gathers on all host threads; mode 0: the reference's own threading (sweeps serial)."""
     import oracle_lib as O
 
     nsw, t = 0, 0.0
@@ -129,11 +144,33 @@ def cpu_sweep_sample(pb, pv4, sen12, blocks, per_block, step, nthreads):
         hi = min(lo + per_block, g1)
         nrays = 16 * (hi - lo) * 2 + 16
         t0 = time.perf_counter()
-        r = O.calsurfg_pre(pb, pv4, sen12, lo, hi, nthreads=nthreads, mode=1, maxnar=nrays * 9000)
+        r = O.calsurfg_pre(pb, pv4, sen12, lo, hi, nthreads=nthreads, mode=mode, maxnar=nrays * 9000)
         t += time.perf_counter() - t0
         assert r["err"] == 0
         nsw += r["nsweeps"]
     return nsw, t
+
+
+def cpu_dispersion_sample(pb, cores):
+    """Oracle depthkernel (K1) on a strip of the model: 4 model rows x nx columns, Rayleigh phase, the workload's
+    periods.  The reference parallelises over model rows (OpenMP, CalSurfG.f90:39-44), so mode (i) here = 4 threads;
+    mode (ii) = the same strip cut into single columns over all host threads."""
+    import oracle_lib as O
+
+    rows = 4
+    vel = np.ascontiguousarray(pb.vsf.reshape(pb.nz, pb.ny, pb.nx)[:, :rows, :])
+    t = np.asarray(pb.tRc if pb.kmaxRc else pb.tLc, np.float64)
+    out = {}
+    for label, nth in (("reference_threading", min(rows, cores)), ("all_cores", cores)):
+        # (nz, ny, nx): the oracle, like the reference, runs its OpenMP loop over the ny model rows
+        v = vel if label == "reference_threading" else np.ascontiguousarray(vel.reshape(pb.nz, rows * pb.nx, 1))
+        t0 = time.perf_counter()
+        O.depthkernel(v, 2, 0, t, pb.depz, pb.minthk, nthreads=nth)
+        dt = time.perf_counter() - t0
+        roots = rows * pb.nx * (1 + 6 * pb.nz) * len(t)
+        out[label] = dict(period_roots_per_s=roots / dt, threads=nth, seconds=dt)
+    out["sample"] = f"depthkernel (Rayleigh phase, {len(t)} periods) on {rows} model rows x {pb.nx} columns"
+    return out
 
 
 def run_reference(args, pb, pv4, sen12, blocks):
@@ -153,12 +190,13 @@ def run_reference(args, pb, pv4, sen12, blocks):
         if s == 0 and t * (args.warmup + args.steps) > 240:  # keep the whole run within minutes
             per_block = max(1, per_block // 2)
     value = nsw_tot / t_tot
-    sample = f"{per_block} gathers of each of {len(blocks)} data types per step, all {cores} host threads"
+    sample = (f"{per_block} gathers of each of {len(blocks)} data types per step (a bounded sample of the step, not a "
+              f"whole step), all {cores} host threads over independent gathers (mode ii); C++ restatement of the "
+              "reference, g++ -O3 -fopenmp strict IEEE -- not gfortran (no Fortran compiler in this image)")
     out = dict(metric=METRIC, value=value, unit="sweeps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-               ms_per_step=1e3 * t_tot / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+               ms_per_step=1e3 * t_tot / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                dtype="f32", data="synthetic", impl="reference",
-               config=dict(workload=pb.name, note="C++ restatement of reference (g++ -O3 -fopenmp, strict IEEE), "
-                           "not gfortran; bounded sample of the same workload"),
+               config=make_config(pb, args.gpus, args.step_mode),
                cpu_baseline=dict(value=value, unit="sweeps/s", cores=cores, kind="port", sample=sample),
                e2e=dict(value=value, unit="sweeps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
@@ -169,16 +207,18 @@ def run_reference(args, pb, pv4, sen12, blocks):
 def run_b200(args, pb, pv4, sen12, blocks, tblocks):
     import torch
 
-    from dsurftomo_b200 import api, dist as ddist, hostglue
+    from dsurftomo_b200 import api, dist as ddist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    comm = None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = ddist.NcclComm(rank, world, local)
     else:
         dist = None
 
@@ -211,26 +251,38 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
     nb = len(blocks)
 
     def block_of(step):
-        return blocks[(step * world + rank) % nb]
+        """This rank's contiguous share of the step's gathers (strong scaling: the step is the same for every N)."""
+        _, b0, b1 = blocks[step % nb]
+        if args.step_mode == "stage":
+            return ddist.shard_gathers(pb, rank, world)
+        lo, hi = ddist.shard_range(b1 - b0, rank, world)
+        return b0 + lo, b0 + hi
 
-    # ---------------- timed region 1: device-resident sweep stage (CUDA events on the launching stream)
+    # ---------------- timed region 1: device-resident sweep stage + the NCCL gather of predicted times and COO row
+    # blocks to every rank (CUDA events on the launching stream, max over ranks)
     sampler = ClockSampler(local)
-    dev_ms, eik_ms, nsw_local, launches, wall, launches_eik, nrays_local = 0.0, 0.0, 0, 0, 0.0, 0, 0
+    dev_ms, eik_ms, gat_ms, nsw_local, launches, wall, launches_eik, nrays_local = 0.0, 0.0, 0.0, 0, 0, 0.0, 0, 0
     stage = dict(eikonal_ms=0.0, rays_ms=0.0, assembly_ms=0.0)
+    nar_total, digest = 0, None
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
             barrier()
             if rank == 0:
                 sampler.start()
             w0 = time.perf_counter()
-        _, g0, g1 = block_of(s)
+        g0, g1 = block_of(s)
         plan.reset_rows()
         plan.sweeps(g0, g1)
+        if comm is not None:
+            nar_total = plan.allgather(comm, want_coo=True)
+        else:
+            nar_total = plan.nar
         if s >= args.warmup:
             r0_, r1_ = ddist.rows_of_gathers(pb, g0, g1)
             nrays_local += r1_ - r0_
             tm = plan.timings()
-            dev_ms += tm["total_ms"]
+            dev_ms += tm["total_ms"] + (plan.gather_ms if comm is not None else 0.0)
+            gat_ms += plan.gather_ms if comm is not None else 0.0
             eik_ms += tm["eikonal_ms"]
             nsw_local += tm["sweeps"]
             launches += tm["launches"]
@@ -240,6 +292,7 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
     barrier()
     wall = time.perf_counter() - w0
     clocks = sampler.stop() if rank == 0 else None
+    digest = plan.digest(gathered=comm is not None)  # equal on 1 and on N GPUs <=> identical COO in identical order
     t_max_ms = maxreduce(dev_ms)
     nsw_total = sumreduce(nsw_local)
     value = nsw_total / (t_max_ms / 1e3)
@@ -250,29 +303,34 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
     n_eik_launches = max(1, int(round(launches_eik)))
     mt = measured_traffic()
     traffic = None
-    if mt and pb.nx == 131:  # measured at cfg 3 only
+    lps = os.environ.get("DSURF_EIKONAL_LPS") is not None
+    if mt and pb.nx == 131 and not lps:  # measured at cfg 3 only, default kernel
         traffic = mt["eikonal"]["dram_bytes_per_sweep"] * nsw_local / n_eik_launches
-    roofline = dict(bound="hbm", kernel="k_eikonal3<16> (+ node-state fill)", achieved=achieved, peak=peak, unit="GB/s",
+    roofline = dict(bound="hbm", kernel=("k_refine<16> + k_march_lps" if lps else "k_eikonal3<16> (+ node-state fill)"),
+                    achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_sweep=b_sweep, algorithmic_bytes_per_launch=b_sweep * nsw_local / n_eik_launches,
                     launches=n_eik_launches, avg_launch_ms=eik_ms / n_eik_launches,
                     traffic_source=(mt["eikonal"]["source"] if traffic else None),
-                    note="issue-bound exact-order FMM replay; DRAM traffic ~250x the algorithmic bytes; see DESIGN.md section 4")
+                    note="exact-order FMM replay: bound by dependent scattered accesses (issue slots of the serial heap "
+                         "work, then DRAM sector rate), not by the algorithmic bytes; DRAM traffic ~250x B_sweep; see "
+                         "DESIGN.md section 4")
 
-    # ---------------- timed region 2: end to end through the host-buffer API (H2D + compute + D2H)
-    last = plan.download()  # sizes the pinned output buffers from the last timed step
-    cap = int(last["nar"] * (1.05 if args.step_mode == "stage" else 1.6)) + 1024
-    pin = dict(row=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
-               col=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
-               rw=torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy(),
-               dsurf=torch.empty(max(pb.dall, 1), dtype=torch.float32, pin_memory=True).numpy())
+    # ---------------- timed region 2: end to end through the host-buffer API (H2D + compute + gather + D2H on rank 0)
+    cap = int(nar_total * (1.05 if args.step_mode == "stage" else 1.6)) + 1024
+    pin = None
+    if rank == 0:
+        pin = dict(row=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+                   col=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+                   rw=torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy(),
+                   dsurf=torch.empty(max(pb.dall, 1), dtype=torch.float32, pin_memory=True).numpy())
     h2d = pb.vsf.nbytes + sum(a.nbytes for a in pv4) + sum(a.nbytes for a in sen12 if a is not None) + \
         pb.scxf.nbytes * 2 + pb.rcxf.nbytes * 2
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 5))
     e2e_t, e2e_sw, d2h = 0.0, 0, 0
     barrier()
     for s in range(e2e_steps):
-        _, g0, g1 = block_of(args.warmup + s)
+        g0, g1 = block_of(args.warmup + s)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         plan.set_model(pb.vsf)                                   # H2D: model
@@ -284,46 +342,38 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         plan.finalize_dispersion()
         plan.reset_rows()
         plan.sweeps(g0, g1)
-        res = plan.download(out=pin)                             # D2H: predicted times + COO rows
+        if comm is not None:
+            ntot = plan.allgather(comm, want_coo=True)
+            if rank == 0:                                        # D2H: the caller's full (rw, iw, col) + predicted times
+                lib_ = api.lib()
+                import ctypes as C
+                api.check(lib_.dsurf_plan_download_gathered(plan.h, api.ptr(pin["row"], C.c_int), api.ptr(pin["rw"], C.c_float),
+                                                            api.ptr(pin["col"], C.c_int)), "download_gathered")
+                api.check(lib_.dsurf_plan_download(plan.h, None, None, None, api.ptr(pin["dsurf"], C.c_float), None),
+                          "download_dsurf")
+        else:
+            ntot = plan.download(out=pin)["nar"]                 # D2H: predicted times + COO rows
         torch.cuda.synchronize()
+        barrier()
         e2e_t += time.perf_counter() - t0
         e2e_sw += plan.timings()["sweeps"]
-        d2h = 12 * res["nar"] + 4 * pb.dall
+        d2h = 12 * ntot + 4 * pb.dall
     e2e_tmax = maxreduce(e2e_t)
     e2e_value = sumreduce(e2e_sw) / e2e_tmax
 
-    # ---------------- LSMR on the rows of the last block (device-resident, then host-buffer call)
+    # ---------------- LSMR on the FULL system of the step (every data row + every smoothing row, main.f90:418-489),
+    # row-partitioned over the ranks exactly as the rows were produced; built on the device from the plans' COO
     lsmr = None
-    if args.lsmr_iters > 0:
-        res = plan.download(out=pin)
-        # system = the data rows of one data-type block (the first one in stage mode) + smoothing rows
-        lb = tblocks[0] if args.step_mode == "stage" else block_of(args.warmup + e2e_steps - 1)
-        r0, r1 = ddist.rows_of_gathers(pb, lb[1], lb[2])
-        lo = int(np.searchsorted(res["row"], r0, side="right"))
-        hi = int(np.searchsorted(res["row"], r1, side="right"))
-        nrows = r1 - r0
-        rows = (res["row"][lo:hi] - r0).astype(np.int32)
-        res = dict(res, col=res["col"][lo:hi], rw=res["rw"][lo:hi])
-        obst = pb.obst[r0:r0 + nrows]
-        cb = (obst - res["dsurf"][r0:r0 + nrows]).astype(np.float32)
-        srow, scol, sval, cnt3 = hostglue.smoothing_rows(pb.nx, pb.ny, pb.nz, nrows, pb.weight)
-        if world > 1:  # smoothing rows are shared out round-robin
-            keep = ((srow - nrows - 1) % world) == rank
-            srow, scol, sval = srow[keep], scol[keep], sval[keep]
-            _, srow = np.unique(srow, return_inverse=True)
-            srow = (srow + nrows + 1).astype(np.int32)
-            cnt3 = int(srow.max() - nrows) if len(srow) else 0
-        R = np.concatenate([rows, srow])
-        Cc = np.concatenate([res["col"], scol])
-        V = np.concatenate([res["rw"], sval])
-        b = np.concatenate([cb, np.zeros(cnt3, np.float32)])
-        m, n = nrows + cnt3, pb.maxvp
+    if args.lsmr_iters > 0 and args.step_mode == "stage":
+        g0, g1 = block_of(0)
+        if comm is None:
+            plan.reset_rows()
+            plan.sweeps(g0, g1)      # fresh, unscaled rows (the e2e loop left them unscaled too; keep it explicit)
         t0 = time.perf_counter()
-        sysl = api.LsmrSystem(m, n, R, Cc, V, b)
+        sysl = api.LsmrSystem.from_plan_shard(plan, rank, world)
         t_build = time.perf_counter() - t0
-        comm = None
-        if world > 1:
-            comm = ddist.NcclComm(rank, world, local)
+        m, n = sysl.m, sysl.n
+        if comm is not None:
             ddist.attach(sysl, comm)
         sysl.solve(pb.damp, itnlim=3, force_iters=True, want_x=False)  # warm-up
         barrier()
@@ -335,29 +385,22 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         ach = lsmr_bytes(sysl.nnz, m, n) * L["itn"] / (L["ms_total"] / 1e3) / 1e9
         ach_spmv = 8.0 * sysl.nnz * L["itn"] / (L["ms_spmv"] / 1e3) / 1e9
         ach_spmtv = 8.0 * sysl.nnz * L["itn"] / (L["ms_spmtv"] / 1e3) / 1e9
-        # host-buffer LSMR call (H2D of the COO, CSR/CSC build, iterations, D2H of x)
-        t0 = time.perf_counter()
-        x = None
-        if world == 1:
-            iw = hostglue.pack_iw(R, Cc)
-            Lh = api.LSMR(m, n, len(iw), len(V), iw, V, b, pb.damp, 1e-6, 1e-6, 100.0, 400, 10)
-            t_host = time.perf_counter() - t0
-            host = dict(iters=Lh["itn"], istop=Lh["istop"], seconds=t_host, iters_per_s=Lh["itn"] / t_host,
-                        h2d_bytes=12 * len(V) + 4 * m, d2h_bytes=4 * n)
-        else:
-            host = None
+        # convergence run with the reference's stopping rules (main.f90:474-485)
+        Lc = sysl.solve(pb.damp, itnlim=400, want_x=False)
+        t_conv = maxreduce(Lc["ms_total"]) / 1e3
         lsmr = dict(iters_per_s=it_s, iters=L["itn"], nnz=int(nnz_tot), m=int(m_tot), n=n, build_s=t_build,
+                    system="full: all data rows of the step + all smoothing rows, row-partitioned over the ranks",
+                    per_rank=dict(nnz=int(sysl.nnz), m=int(m)),
                     roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                                   spmv_gbs=ach_spmv, spmtv_gbs=ach_spmtv,
                                   traffic=(mt["lsmr"]["dram_bytes_per_nnz_per_iter"] * sysl.nnz if mt else None),
                                   traffic_source=(mt["lsmr"]["source"] if mt else None),
                                   algorithmic_bytes_per_iter=lsmr_bytes(sysl.nnz, m, n),
-                                  note="depth-blocked layout stores 1 index + 8 values per vertex: real bytes are "
-                                       "~0.58x the algorithmic 16 B per non-zero"),
-                    launches_per_iter=(6 if world == 1 else 9), host_buffer_call=host)
+                                  note="per rank; depth-blocked layout stores 1 index + 8 values per vertex: real bytes "
+                                       "are ~0.58x the algorithmic 16 B per non-zero"),
+                    launches_per_iter=(6 if world == 1 else 9),
+                    to_convergence=dict(iters=Lc["itn"], istop=Lc["istop"], seconds=t_conv, normr=Lc["normr"]))
         sysl.close()
-        if comm:
-            comm.close()
 
     # ---------------- K1: dispersion + depth kernels of the whole model (FP64-bound)
     disp = None
@@ -371,54 +414,69 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         # curve evaluations: every column x (1 + 6 nz) model variants x periods; group-velocity
         # types evaluate two phase curves per period (surfdisp96.f:227-229)
         curves = ncol * (1 + 6 * pb.nz) * sum(k * (2 if t in (1, 3) else 1) for t, k in enumerate(kts))
+        dp_per_root = 3.4e5  # FP64 operations per period root, from profiles/r01_disp_cfg3.md (pipe-active cycles x lanes)
         disp = dict(ms=dms, columns=ncol, column_types_per_s=ncol * sum(1 for k in kts if k) / (dms / 1e3),
                     period_roots_per_s=curves / (dms / 1e3), bound="fp64 alu/sfu",
+                    dp_gflops_est=curves / (dms / 1e3) * dp_per_root / 1e9,
+                    dp_gflops_note="period roots/s x 3.4e5 FP64 operations per root (ncu FP64-pipe-active cycles of the "
+                                   "Rayleigh-phase run in profiles/r01_disp_cfg3.md; no FMA: --fmad=false)",
                     note="depthkernel for all data types of the model (one CalSurfG dispersion stage), 1 launch set")
 
-    # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores
+    # ---------------- CPU baseline (rank 0, N = 1 only): bounded samples on the host cores
     cpu = None
     if world == 1 and not args.no_cpu:
-        import oracle_lib as O
-
         cores = os.cpu_count() or 1
         per_block = 128  # ~10 s of CPU work on 16 host threads (fewer seconds on more cores)
-        nsw, t = cpu_sweep_sample(pb, pv4, sen12, tblocks, per_block, 0, cores)
+        nsw, t = cpu_sweep_sample(pb, pv4, sen12, tblocks, per_block, 0, cores, mode=1)
+        nsw1, t1 = cpu_sweep_sample(pb, pv4, sen12, tblocks, 2, 0, 1, mode=1)
         cpu = dict(value=nsw / t, unit="sweeps/s", cores=cores, kind="port",
-                   sample=f"{per_block} gathers of each of {len(tblocks)} data types ({nsw} sweeps, {t:.1f} s), "
-                          "C++ restatement of the reference, g++ -O3 -fopenmp strict IEEE (no Fortran compiler here)")
-        if lsmr is not None and lsmr["nnz"] <= 3e8:
-            iw = hostglue.pack_iw(R, Cc)
-            t0 = time.perf_counter()
-            Lc = O.lsmr(m, n, iw, V, b, pb.damp, itnlim=3)
-            tl = time.perf_counter() - t0
-            cpu["lsmr_iters_per_s"] = Lc["itn"] / tl
-            cpu["lsmr_sample"] = f"{Lc['itn']} iterations of the same system, 1 thread (the reference's LSMR is serial)"
+                   sample=f"{per_block} gathers of each of {len(tblocks)} data types ({nsw} sweeps, {t:.1f} s), all host "
+                          "threads over independent gathers (mode ii); C++ restatement of the reference, g++ -O3 -fopenmp "
+                          "strict IEEE (no Fortran compiler here)",
+                   reference_threading=dict(value=nsw1 / t1, unit="sweeps/s", cores=1,
+                                            sample=f"{nsw1} sweeps on one thread ({t1:.1f} s): the reference marches its "
+                                                   "sources serially (mode i, CalSurfG.f90:1144-1145)"))
+        if disp is not None:
+            cpu["dispersion"] = cpu_dispersion_sample(pb, cores)
 
     if rank == 0:
+        cfg = make_config(pb, world, args.step_mode)
         out = dict(metric=METRIC, value=value, unit="sweeps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                   ms_per_step=t_max_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                   dtype="f32", data="synthetic",
-                   config=dict(workload=pb.name, grid=f"{(pb.nx - 3) * 8 + 1}x{(pb.ny - 3) * 8 + 1}",
-                               step=("one full CalSurfG sweep stage (every period x type x source) per rank per step"
-                                     if args.step_mode == "stage" else
-                                     "all periods x sources of one data type per rank per step "
-                                     f"({[b[0] for b in blocks]} in rotation)"),
-                               receivers_per_gather=int(pb.nrc1.max()), parallelism=f"gathers sharded over {world} GPU(s)",
-                               l2="per-step working set (node states of thousands of sweeps, GBs) >> 126 MB L2",
-                               interpretation="A: quoted grid = FMM propagation grid (SURVEY.md section 8)"),
+                   ms_per_step=t_max_ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                   dtype="f32", data="synthetic", config=cfg,
+                   parallelism=(f"gathers sharded over {world} GPU(s) in contiguous blocks; per step one NCCL all-gather of "
+                                "the predicted times and of the COO row blocks (counts, then grouped broadcasts) inside the "
+                                "timed region" if world > 1 else "1 GPU: no exchange"),
                    roofline=roofline, cpu_baseline=cpu,
                    e2e=dict(value=e2e_value, unit="sweeps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                            steps=e2e_steps, api="Plan.set_model/set_dispersion/sweeps/download through the C ABI "
-                                                 "with host buffers (pinned outputs)"),
+                            steps=e2e_steps, api="Plan.set_model/set_dispersion/sweeps/[allgather]/download through the "
+                                                 "C ABI with host buffers (pinned outputs on rank 0)"),
                    gpu_launches=int(launches), clocks=clocks,
-                   stage_ms_per_step={k: v / args.steps for k, v in stage.items()}, wall_s_timed=wall,
+                   stage_ms_per_step=dict({k: v / args.steps for k, v in stage.items()}, gather_ms=gat_ms / args.steps),
+                   coo=dict(nar=int(nar_total), digest=f"{digest[0]:016x}", digest_n=digest[1],
+                            note="order-sensitive digest of (row, col, rw): equal for every --gpus N"),
+                   wall_s_timed=wall,
                    rays=dict(rays_per_s=(nrays_local / (stage["rays_ms"] / 1e3) if stage["rays_ms"] > 0 else None),
                              rows_per_s=(nrays_local / (stage["assembly_ms"] / 1e3) if stage["assembly_ms"] > 0 else None),
                              note="rank 0: receiver times + ray back-trace (k_rays) and Frechet row assembly, rays per second "
                                   "of their own stage time (SURVEY.md 8d: latency-bound gathers, no HBM fraction quoted)"),
                    lsmr=lsmr, dispersion=disp, impl="b200")
-        emit(out)
     plan.close()
+    # ---------------- e2e through dsurf_calsurfg itself (K1 included), host buffers in and out: the call a Fortran
+    # main program makes (main.f90:355-359).  N = 1 only; its own plan needs the memory the bench plan just released.
+    if rank == 0 and world == 1 and args.calsurfg_e2e and args.step_mode == "stage":
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = api.CalSurfG(pb, maxnar=cap)
+        dt = time.perf_counter() - t0
+        out["e2e_calsurfg"] = dict(value=out["config"]["sweeps_per_step"] / dt, unit="sweeps/s", seconds=dt, steps=1,
+                                   nar=int(res["nar"]),
+                                   note="one dsurf_calsurfg call with host buffers: H2D model, dispersion + depth kernels "
+                                        "(K1) of the real model, sweeps, rays, rows, D2H of (rw, iw, col, dsurf)")
+    if rank == 0:
+        emit(out)
+    if comm is not None:
+        comm.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -452,6 +510,7 @@ def main():
     ap.add_argument("--lsmr-iters", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dispersion", dest="dispersion", action="store_false")
+    ap.add_argument("--no-calsurfg-e2e", dest="calsurfg_e2e", action="store_false")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference" and rank != 0:

@@ -58,6 +58,8 @@ def lib():
     L.dsurf_plan_nar.argtypes = [C.c_void_p]
     L.dsurf_plan_last_sweeps_ms.restype = C.c_double
     L.dsurf_plan_last_sweeps_ms.argtypes = [C.c_void_p]
+    L.dsurf_plan_last_gather_ms.restype = C.c_double
+    L.dsurf_plan_last_gather_ms.argtypes = [C.c_void_p]
     L.dsurf_lsmr_nnz.argtypes = [C.c_void_p]
     for name in ("dsurf_plan_num_gathers", "dsurf_plan_nrows", "dsurf_plan_destroy", "dsurf_plan_dispersion",
                  "dsurf_plan_reset_rows", "dsurf_lsmr_destroy"):

@@ -269,6 +269,30 @@ class Plan:
                                         ptr(dsurf, C.c_float), C.byref(rb)), "plan_download")
         return dict(nar=n, row=rows[:n], rw=rw[:n], col=col[:n], dsurf=dsurf[: self.pb.dall], rbint=rb.value)
 
+    def allgather(self, comm, want_coo=True):
+        """Multi-GPU exchange (dsurf_plan_allgather): predicted times of all rows, and the COO row blocks of every
+        rank in rank order when want_coo.  Returns the total number of triplets."""
+        tot = C.c_int64(0)
+        check(lib().dsurf_plan_allgather(self.h, comm.h, C.c_int(comm.rank), C.c_int(comm.world),
+                                         C.c_int(1 if want_coo else 0), C.byref(tot)), "plan_allgather")
+        return int(tot.value)
+
+    @property
+    def gather_ms(self):
+        return float(lib().dsurf_plan_last_gather_ms(self.h))
+
+    def download_gathered(self, nar):
+        rows, rw, col = np.zeros(max(nar, 1), I32), np.zeros(max(nar, 1), F32), np.zeros(max(nar, 1), I32)
+        check(lib().dsurf_plan_download_gathered(self.h, ptr(rows, C.c_int), ptr(rw, C.c_float), ptr(col, C.c_int)),
+              "plan_download_gathered")
+        return dict(nar=nar, row=rows[:nar], rw=rw[:nar], col=col[:nar])
+
+    def digest(self, gathered=False):
+        """(64-bit order-sensitive digest, number of triplets) of the plan's COO or of the gathered COO."""
+        d, n = C.c_uint64(0), C.c_int64(0)
+        check(lib().dsurf_plan_digest(self.h, C.c_int(1 if gathered else 0), C.byref(d), C.byref(n)), "plan_digest")
+        return int(d.value), int(n.value)
+
     def glue_results(self, want_vectors=True):
         """cbst / datweight / statistics left by LsmrSystem.from_plan (main.f90:361-394)."""
         dall = self.pb.dall
@@ -353,6 +377,21 @@ class LsmrSystem:
         self = cls.__new__(cls)
         g = plan.glue_results(want_vectors=False)
         self.h, self.m, self.n, self.nnz = h, g["m"], pb.maxvp, g["nar"]
+        return self
+
+    @classmethod
+    def from_plan_shard(cls, plan, rank, world, obst=None, threshold0=None, weight=None):
+        """Row-partitioned system of rank `rank` (its own data rows + a share of the smoothing rows); the plan must
+        hold the predicted times of all rows (Plan.allgather)."""
+        pb = plan.pb
+        obst = _c(pb.obst if obst is None else obst, F32)
+        h, m, nnz = C.c_void_p(), C.c_int(0), C.c_int64(0)
+        check(lib().dsurf_lsmr_create_from_plan_shard(
+            C.byref(h), plan.h, ptr(obst, C.c_float), C.c_float(pb.threshold if threshold0 is None else threshold0),
+            C.c_float(pb.weight if weight is None else weight), C.c_int(rank), C.c_int(world), C.byref(m),
+            C.byref(nnz)), "lsmr_create_from_plan_shard")
+        self = cls.__new__(cls)
+        self.h, self.m, self.n, self.nnz = h, m.value, pb.maxvp, nnz.value
         return self
 
     def close(self):

@@ -22,6 +22,8 @@ typedef int (*fn_GetUniqueId)(ncclUniqueId *);
 typedef int (*fn_CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
 typedef int (*fn_CommDestroy)(ncclComm_t);
 typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef int (*fn_Group)(void);
 typedef const char *(*fn_ErrStr)(int);
 struct Nccl {
@@ -30,6 +32,8 @@ struct Nccl {
   fn_CommInitRank CommInitRank = nullptr;
   fn_CommDestroy CommDestroy = nullptr;
   fn_AllReduce AllReduce = nullptr;
+  fn_AllGather AllGather = nullptr;
+  fn_Broadcast Broadcast = nullptr;
   fn_Group GroupStart = nullptr, GroupEnd = nullptr;
   fn_ErrStr ErrStr = nullptr;
 } g;
@@ -50,10 +54,13 @@ int load_nccl() {
   g.CommInitRank = (fn_CommInitRank)dlsym(h, "ncclCommInitRank");
   g.CommDestroy = (fn_CommDestroy)dlsym(h, "ncclCommDestroy");
   g.AllReduce = (fn_AllReduce)dlsym(h, "ncclAllReduce");
+  g.AllGather = (fn_AllGather)dlsym(h, "ncclAllGather");
+  g.Broadcast = (fn_Broadcast)dlsym(h, "ncclBroadcast");
   g.GroupStart = (fn_Group)dlsym(h, "ncclGroupStart");
   g.GroupEnd = (fn_Group)dlsym(h, "ncclGroupEnd");
   g.ErrStr = (fn_ErrStr)dlsym(h, "ncclGetErrorString");
-  if (!g.GetUniqueId || !g.CommInitRank || !g.CommDestroy || !g.AllReduce || !g.GroupStart || !g.GroupEnd) {
+  if (!g.GetUniqueId || !g.CommInitRank || !g.CommDestroy || !g.AllReduce || !g.AllGather || !g.Broadcast ||
+      !g.GroupStart || !g.GroupEnd) {
     dsurf::set_error(__FILE__, __LINE__, "libnccl lacks an expected symbol");
     return DSURF_ERR_NCCL;
   }
@@ -68,14 +75,37 @@ int nccl_check(int rc, int line) {
 }  // namespace
 
 namespace dsurf {
+// the group is always closed, also when a call inside it failed (an open group would poison every later NCCL call)
 int lsmr_allreduce(void *comm, float *buf, size_t n, double *dbuf, size_t nd, cudaStream_t st) {
   if (!comm) return DSURF_OK;
   DS_CHECK(load_nccl());
   DS_CHECK(nccl_check(g.GroupStart(), __LINE__));
-  if (n) DS_CHECK(nccl_check(g.AllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)comm, st), __LINE__));
-  if (nd) DS_CHECK(nccl_check(g.AllReduce(dbuf, dbuf, nd, ncclFloat64, ncclSum, (ncclComm_t)comm, st), __LINE__));
-  DS_CHECK(nccl_check(g.GroupEnd(), __LINE__));
-  return DSURF_OK;
+  int rc = DSURF_OK;
+  if (n) rc = nccl_check(g.AllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)comm, st), __LINE__);
+  if (nd && rc == DSURF_OK) rc = nccl_check(g.AllReduce(dbuf, dbuf, nd, ncclFloat64, ncclSum, (ncclComm_t)comm, st), __LINE__);
+  const int rc2 = nccl_check(g.GroupEnd(), __LINE__);
+  return rc != DSURF_OK ? rc : rc2;
+}
+
+// ---- exchange of the forward/sensitivity path: every rank contributes one block
+int nccl_allgather_bytes(void *comm, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t st) {
+  DS_CHECK(load_nccl());
+  return nccl_check(g.AllGather(send, recv, bytes_per_rank, /*ncclInt8*/ 0, (ncclComm_t)comm, st), __LINE__);
+}
+// grouped broadcasts: block r (count4[r] 32-bit words at recv + off4[r]) comes from rank r; `send` is this rank's block
+int nccl_allgatherv_words(void *comm, int rank, int nranks, const void *send, void *recv, const long long *off4,
+                          const long long *count4, cudaStream_t st) {
+  DS_CHECK(load_nccl());
+  DS_CHECK(nccl_check(g.GroupStart(), __LINE__));
+  int rc = DSURF_OK;
+  for (int r = 0; r < nranks && rc == DSURF_OK; r++) {
+    if (count4[r] <= 0) continue;
+    char *dst = (char *)recv + 4 * off4[r];
+    rc = nccl_check(g.Broadcast(r == rank ? send : (const void *)dst, dst, (size_t)count4[r], ncclFloat32, r, (ncclComm_t)comm, st),
+                    __LINE__);
+  }
+  const int rc2 = nccl_check(g.GroupEnd(), __LINE__);
+  return rc != DSURF_OK ? rc : rc2;
 }
 }  // namespace dsurf
 

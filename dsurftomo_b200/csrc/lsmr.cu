@@ -1687,9 +1687,21 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   const float ctol = conlim > 0.0f ? 1.0f / conlim : 0.0f;
   const bool dist = s->comm != nullptr && s->nranks > 1;
   choose_fused(s);
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  // events and the iteration graph are released on every return path, error paths included
+  struct Guard {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    ~Guard() {
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+    }
+  } guard;
+  cudaEventCreate(&guard.e0);
+  cudaEventCreate(&guard.e1);
+  cudaEvent_t e0 = guard.e0, e1 = guard.e1;
   DS_CUDA(cudaMemsetAsync(S, 0, sizeof(LsmrScalars), st));
   DS_CUDA(cudaMemsetAsync(s->x.p, 0, (size_t)n * sizeof(float), st));
   DS_CUDA(cudaMemsetAsync(s->hbar.p, 0, (size_t)n * sizeof(float), st));
@@ -1722,8 +1734,8 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   // ---- main loop.  Single GPU: the iteration is captured once into a CUDA graph and replayed;
   // every kernel no-ops once the device-side stop flag is set, so the host only polls the flag
   // every kPoll iterations (the solution is frozen at the exact stopping iteration).
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
+  cudaGraph_t &graph = guard.graph;
+  cudaGraphExec_t &gexec = guard.gexec;
   const bool use_graph = !dist && getenv("DSURF_LSMR_NO_GRAPH") == nullptr;
   if (use_graph && !h_stop) {
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -1766,8 +1778,6 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   if (x_host) DS_CUDA(cudaMemcpyAsync(x_host, s->xout.p, (size_t)s->n * sizeof(float), cudaMemcpyDeviceToHost, st));
   DS_CUDA(cudaStreamSynchronize(st));
   DS_CUDA(cudaGetLastError());
-  if (gexec) cudaGraphExecDestroy(gexec);
-  if (graph) cudaGraphDestroy(graph);
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_total) *ms_total = ms;
@@ -1791,8 +1801,6 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
       *dst = (double)ms / reps * (double)hs.itn;  // scaled to the iteration count like before
     }
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   int is = hs.istop;
   if (damp > 0.0f && is == 2) is = 3;  // lsmrModule.f90:654
   if (istop) *istop = is;

@@ -101,6 +101,13 @@ struct dsurf_plan {
   DevBuf<float> dsurf, rw;
   DevBuf<int> col, rowidx, flags;  // flags[0] err, flags[1] rbint
   long long nar = 0;
+  int last_g0 = 0, last_g1 = 0;  // gather range of the rows currently in the COO (dsurf_plan_sweeps)
+  // multi-GPU: COO of every rank in rank order (dsurf_plan_allgather)
+  DevBuf<float> G_rw;
+  DevBuf<int> G_col, G_row;
+  DevBuf<long long> G_cnt;
+  long long G_nar = -1;
+  double ms_gather = 0;
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evt0 = nullptr, evt1 = nullptr;
@@ -790,6 +797,9 @@ extern "C" int dsurf_plan_sweeps(dsurf_plan *p, int g0, int g1) {
   g0 = std::max(g0, 0);
   g1 = std::min(g1, (int)p->gathers.size());
   for (int i = 2; i < 8; i++) p->ms[i] = 0;
+  if (p->nar == 0) p->last_g0 = g0;  // rows accumulate until dsurf_plan_reset_rows
+  p->last_g1 = g1;
+  p->G_nar = -1;
   int launches = 0, nsolved = 0;
   cudaEventRecord(p->evt0, p->st);
   std::vector<SweepDesc> hsw;
@@ -1084,6 +1094,108 @@ extern "C" void synthetic_(const int *nx, const int *ny, const int *nz, const in
   }
 }
 
+// ------------------------------------------------------------------- multi-GPU exchange
+namespace dsurf {
+int nccl_allgather_bytes(void *comm, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t st);
+int nccl_allgatherv_words(void *comm, int rank, int nranks, const void *send, void *recv, const long long *off4,
+                          const long long *count4, cudaStream_t st);
+}
+static int first_row_of(const dsurf_plan *p, int g) { return g < (int)p->gathers.size() ? p->gathers[g].first_row : p->dall; }
+
+// Ranks hold contiguous gather blocks in rank order (the loop nest CalSurfG.f90:1144-1145 cut into blocks), so the
+// reference's output is the concatenation of the ranks' outputs: one all-gather of the predicted times (every rank
+// needs them for the percentile weights of main.f90:361-376) and, when the caller wants the full COO that
+// main.f90:355-359 receives, one of the row blocks -- counts first, then grouped broadcasts straight into place.
+extern "C" int dsurf_plan_allgather(dsurf_plan *p, void *comm, int rank, int nranks, int want_coo, int64_t *nar_total) {
+  if (!p || !comm || rank < 0 || rank >= nranks || nranks > 64) return DSURF_ERR_BAD_ARG;
+  cudaStream_t st = p->st;
+  cudaEventRecord(p->ev[0], st);
+  if (p->G_cnt.reserve(4 * 66)) return DSURF_ERR_CUDA;
+  long long mine[4] = {p->nar, first_row_of(p, p->last_g0), first_row_of(p, p->last_g1), 0};
+  DS_CUDA(cudaMemcpyAsync(p->G_cnt.p + 4 * 64, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  DS_CHECK(nccl_allgather_bytes(comm, p->G_cnt.p + 4 * 64, p->G_cnt.p, sizeof(mine), st));
+  long long all[4 * 64];
+  DS_CUDA(cudaMemcpyAsync(all, p->G_cnt.p, sizeof(long long) * 4 * nranks, cudaMemcpyDeviceToHost, st));
+  DS_CUDA(cudaStreamSynchronize(st));
+  long long off[64], cnt[64], roff[64], rcnt[64], tot = 0;
+  for (int r = 0; r < nranks; r++) {
+    off[r] = tot;
+    cnt[r] = all[4 * r];
+    tot += cnt[r];
+    roff[r] = all[4 * r + 1];
+    rcnt[r] = all[4 * r + 2] - all[4 * r + 1];
+    if (r > 0 && roff[r] != all[4 * (r - 1) + 2]) {
+      set_error(__FILE__, __LINE__, "allgather: the ranks' gather blocks are not contiguous in rank order");
+      return DSURF_ERR_BAD_ARG;
+    }
+  }
+  // predicted times: in place, every rank's slice of the full-length vector
+  DS_CHECK(nccl_allgatherv_words(comm, rank, nranks, p->dsurf.p + roff[rank], p->dsurf.p, roff, rcnt, st));
+  p->G_nar = -1;
+  if (want_coo) {
+    if (p->G_rw.reserve((size_t)std::max<long long>(tot, 1)) || p->G_col.reserve((size_t)std::max<long long>(tot, 1)) ||
+        p->G_row.reserve((size_t)std::max<long long>(tot, 1))) {
+      set_error(__FILE__, __LINE__, "cudaMalloc failed (gathered COO)");
+      return DSURF_ERR_CUDA;
+    }
+    DS_CHECK(nccl_allgatherv_words(comm, rank, nranks, p->rw.p, p->G_rw.p, off, cnt, st));
+    DS_CHECK(nccl_allgatherv_words(comm, rank, nranks, p->col.p, p->G_col.p, off, cnt, st));
+    DS_CHECK(nccl_allgatherv_words(comm, rank, nranks, p->rowidx.p, p->G_row.p, off, cnt, st));
+    p->G_nar = tot;
+  }
+  cudaEventRecord(p->ev[1], st);
+  DS_CUDA(cudaStreamSynchronize(st));
+  DS_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+  p->ms_gather = ms;
+  if (nar_total) *nar_total = tot;
+  return DSURF_OK;
+}
+extern "C" double dsurf_plan_last_gather_ms(const dsurf_plan *p) { return p ? p->ms_gather : 0.0; }
+
+extern "C" int dsurf_plan_download_gathered(dsurf_plan *p, int *iw_rows, float *rw, int *col) {
+  if (!p || p->G_nar < 0) return DSURF_ERR_BAD_ARG;
+  const size_t n = (size_t)p->G_nar;
+  if (n == 0) return DSURF_OK;
+  if (iw_rows) DS_CUDA(cudaMemcpy(iw_rows, p->G_row.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (rw) DS_CUDA(cudaMemcpy(rw, p->G_rw.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (col) DS_CUDA(cudaMemcpy(col, p->G_col.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  return DSURF_OK;
+}
+
+// position-keyed 64-bit digest of a COO (order-sensitive): equal digests on 1 and on N GPUs <=> same triplets in the same order
+__global__ void k_coo_digest(const int *__restrict__ row, const int *__restrict__ col, const float *__restrict__ rw,
+                             long long n, unsigned long long *out) {
+  unsigned long long acc = 0;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    unsigned long long h = (unsigned long long)k * 0x9E3779B97F4A7C15ull;
+    h ^= ((unsigned long long)(unsigned)row[k] << 32) | (unsigned)col[k];
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= (unsigned long long)__float_as_uint(rw[k]) * 0x94D049BB133111EBull;
+    h ^= h >> 29;
+    acc += h;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+extern "C" int dsurf_plan_digest(dsurf_plan *p, int gathered, uint64_t *digest, int64_t *n_out) {
+  if (!p || !digest || (gathered && p->G_nar < 0)) return DSURF_ERR_BAD_ARG;
+  const long long n = gathered ? p->G_nar : p->nar;
+  if (p->G_cnt.reserve(4 * 66)) return DSURF_ERR_CUDA;
+  unsigned long long *d = reinterpret_cast<unsigned long long *>(p->G_cnt.p + 4 * 64 + 4);
+  DS_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), p->st));
+  if (n > 0)
+    k_coo_digest<<<sm_count() * 8, 256, 0, p->st>>>(gathered ? p->G_row.p : p->rowidx.p, gathered ? p->G_col.p : p->col.p,
+                                                    gathered ? p->G_rw.p : p->rw.p, n, d);
+  unsigned long long h = 0;
+  DS_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, p->st));
+  DS_CUDA(cudaStreamSynchronize(p->st));
+  *digest = h;
+  if (n_out) *n_out = n;
+  return DSURF_OK;
+}
+
 // ------------------------------------------------------------------- device-resident host glue
 // main.f90:361-466 on the device: residual, percentile outlier weights, row scaling, DWS statistics,
 // smoothing rows appended behind the data rows, then the LSMR system is built straight from the
@@ -1136,6 +1248,76 @@ extern "C" int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **sys, dsurf_plan *p, 
   DS_CUDA(cudaStreamSynchronize(st));
   p->g_valid = true;
   return lsmr_sys_create_dev(sys, m, maxvp, nnz, p->rowidx.p, p->col.p, p->rw.p, p->g_cbst.p);
+}
+
+// Row-partitioned variant for the distributed LSMR: this rank keeps the data rows it produced
+// (gathers [last_g0, last_g1)) plus a contiguous share of the smoothing rows; rows are renumbered 1..m_local.  The
+// predicted times of ALL rows must be present (dsurf_plan_allgather) because the outlier weights use the percentiles
+// of every residual (main.f90:361-376).  With nranks == 1 this is dsurf_lsmr_create_from_plan.
+__global__ void k_shift_rows(int *rows, long long n, int delta) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) rows[k] += delta;
+}
+extern "C" int dsurf_lsmr_create_from_plan_shard(dsurf_lsmr_sys **sys, dsurf_plan *p, const float *obst, float threshold0,
+                                                 float weight, int rank, int nranks, int *m_local, int64_t *nnz_local) {
+  if (!sys || !p || !obst || rank < 0 || rank >= nranks) return DSURF_ERR_BAD_ARG;
+  DS_CHECK(ensure_device());
+  const int dall = p->dall;
+  const int maxvp = p->g.nvx * p->g.nvz * (p->nz - 1);
+  if (dall < 2) return DSURF_ERR_BAD_ARG;
+  cudaStream_t st = p->st;
+  const int R0 = first_row_of(p, p->last_g0), R1 = first_row_of(p, p->last_g1);
+  std::vector<int> r, c;
+  std::vector<float> v;
+  int count3 = 0;
+  glue_smoothing_rows(p->g.nx, p->g.ny, p->nz, dall, weight, r, c, v, &count3);
+  const int base = count3 / nranks, rem = count3 % nranks;
+  const int s0 = rank * base + std::min(rank, rem), s1 = s0 + base + (rank < rem ? 1 : 0);
+  size_t k0 = 0, k1 = 0;  // triplets of smoothing rows (s0, s1]: rows are ascending
+  while (k0 < r.size() && r[k0] <= dall + s0) k0++;
+  k1 = k0;
+  while (k1 < r.size() && r[k1] <= dall + s1) k1++;
+  const long long nsm = (long long)(k1 - k0);
+  const int mdata = R1 - R0, m = mdata + (s1 - s0);
+  for (size_t k = k0; k < k1; k++) r[k] = r[k] - dall - s0 + mdata;
+  if (p->g_obst.reserve(dall) || p->g_cbst.reserve((size_t)dall + count3) || p->g_datw.reserve(dall) ||
+      p->g_norm.reserve((size_t)maxvp + 2)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (glue vectors)");
+    return DSURF_ERR_CUDA;
+  }
+  DS_CUDA(cudaMemcpyAsync(p->g_obst.p, obst, (size_t)dall * sizeof(float), cudaMemcpyHostToDevice, st));
+  DS_CUDA(cudaMemsetAsync(p->g_cbst.p, 0, ((size_t)dall + count3) * sizeof(float), st));
+  DS_CHECK(glue_apply(st, dall, maxvp, p->nar, p->g_obst.p, p->dsurf.p, threshold0, p->rowidx.p, p->col.p, p->rw.p,
+                      p->g_cbst.p, p->g_datw.p, p->g_norm.p, p->g_sorted, p->g_tmp, &p->g_stats));
+  const long long nnz = p->nar + nsm;
+  if (nnz >= (1ll << 31)) {
+    set_error(__FILE__, __LINE__, "nar exceeds the int32 triplet count of the reference boundary");
+    return DSURF_ERR_CAPACITY;
+  }
+  if (p->rw.reserve((size_t)nnz, true, st) || p->col.reserve((size_t)nnz, true, st) || p->rowidx.reserve((size_t)nnz, true, st)) {
+    set_error(__FILE__, __LINE__, "cudaMalloc failed (COO growth for smoothing rows)");
+    return DSURF_ERR_CUDA;
+  }
+  if (nsm > 0) {
+    DS_CUDA(cudaMemcpyAsync(p->rowidx.p + p->nar, r.data() + k0, (size_t)nsm * sizeof(int), cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemcpyAsync(p->col.p + p->nar, c.data() + k0, (size_t)nsm * sizeof(int), cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemcpyAsync(p->rw.p + p->nar, v.data() + k0, (size_t)nsm * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  // right-hand side: residuals of the local data rows, zeros for the smoothing rows (main.f90:461)
+  DevBuf<float> bl;
+  if (bl.reserve((size_t)std::max(m, 1))) return DSURF_ERR_CUDA;
+  DS_CUDA(cudaMemsetAsync(bl.p, 0, (size_t)std::max(m, 1) * sizeof(float), st));
+  if (mdata > 0) DS_CUDA(cudaMemcpyAsync(bl.p, p->g_cbst.p + R0, (size_t)mdata * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (p->nar > 0 && R0 != 0) k_shift_rows<<<sm_count() * 4, 256, 0, st>>>(p->rowidx.p, p->nar, -R0);
+  DS_CUDA(cudaStreamSynchronize(st));
+  p->g_valid = true;
+  p->g_count3 = count3;
+  p->g_nsm = nsm;
+  const int rc = lsmr_sys_create_dev(sys, m, maxvp, nnz, p->rowidx.p, p->col.p, p->rw.p, bl.p);
+  if (p->nar > 0 && R0 != 0) k_shift_rows<<<sm_count() * 4, 256, 0, st>>>(p->rowidx.p, p->nar, R0);  // global numbering again
+  DS_CUDA(cudaStreamSynchronize(st));
+  if (m_local) *m_local = m;
+  if (nnz_local) *nnz_local = nnz;
+  return rc;
 }
 
 extern "C" int dsurf_plan_glue_results(dsurf_plan *p, float *cbst, float *datweight, float *stats4, int *m_out,

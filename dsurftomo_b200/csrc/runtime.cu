@@ -4,10 +4,12 @@
 #include <mutex>
 #include "../../include/dsurftomo_b200.h"
 #include "common.cuh"
+#include "build_info.h"
 
 namespace dsurf {
 thread_local std::string g_last_error;
 static int g_device = -1;
+static int g_requested_device = -1;  // set by dsurf_set_device (guarded by g_mu through ensure_device)
 static int g_sm_count = 148;
 static std::mutex g_mu;
 
@@ -30,7 +32,10 @@ int ensure_device() {
     return DSURF_ERR_NO_CUDA;
   }
   int dev = 0;
-  if (const char *lr = getenv("LOCAL_RANK")) dev = atoi(lr) % n;
+  if (g_requested_device >= 0)
+    dev = g_requested_device % n;  // dsurf_set_device
+  else if (const char *lr = getenv("LOCAL_RANK"))
+    dev = atoi(lr) % n;  // torchrun's default; only read, never written
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.major < 10) {
     g_last_error = "device is not sm_100-class: libdsurf_b200 is built for sm_100a only";
@@ -52,13 +57,11 @@ extern "C" int dsurf_set_device(int device) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_device = -1;
   }
-  char buf[32];
-  snprintf(buf, sizeof(buf), "%d", device);
-  setenv("LOCAL_RANK", buf, 1);
+  g_requested_device = device;
   return ensure_device();
 }
 extern "C" const char *dsurf_build_info(void) {
-  return "libdsurf_b200: sm_100a, --fmad=false, fp32 eikonal/rays/LSMR, fp64 dispersion search";
+  return "libdsurf_b200: sm_100a, --fmad=false, fp32 eikonal/rays/LSMR, fp64 dispersion search; src " DSURF_SRC_HASH;
 }
 
 static void fatal(int rc, const char *who) {

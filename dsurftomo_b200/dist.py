@@ -104,6 +104,10 @@ def partition_system(sysd: dict, rank: int, world: int):
     target = cum[-1] * np.arange(world + 1) / world
     cuts = np.searchsorted(cum, target, side="left")
     cuts[0], cuts[-1] = 0, m
+    if m < world:
+        raise ValueError(f"partition_system: {m} rows cannot be split over {world} ranks (every rank needs a row)")
+    for r in range(1, world):  # strictly increasing cuts: an empty rank would fail alone and hang the others
+        cuts[r] = min(max(cuts[r], cuts[r - 1] + 1), m - (world - r))
     r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
     sel = (rows > r0) & (rows <= r1)
     return dict(m=r1 - r0, n=sysd["n"], rows=(rows[sel] - r0).astype(np.int32), cols=cols[sel], vals=vals[sel],

@@ -14,8 +14,10 @@ def getpercentile(a):
     """getpercentile.f90: RA(int(0.25*N)), RA(int(0.75*N)) of the ascending sort (1-based)."""
     n = len(a)
     ra = np.sort(np.asarray(a, F32), kind="stable")
-    i25 = int(F32(0.25) * F32(n))
-    i75 = int(F32(0.75) * F32(n))
+    # N < 4 makes the reference read RA(0) (out of bounds): clamp to the first element like the device glue
+    # (glue.cu: glue_percentiles) instead of wrapping to the largest one
+    i25 = max(int(F32(0.25) * F32(n)), 1)
+    i75 = max(int(F32(0.75) * F32(n)), 1)
     return ra[i25 - 1], ra[i75 - 1]
 
 

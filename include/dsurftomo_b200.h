@@ -216,6 +216,19 @@ int dsurf_plan_timings(const dsurf_plan *plan, double *ms8);
 /* device time (ms, CUDA events on the launching stream) of the whole last dsurf_plan_sweeps call */
 double dsurf_plan_last_sweeps_ms(const dsurf_plan *plan);
 
+/* Multi-GPU exchange of the path (one process per GPU; comm = ncclComm_t from dsurf_nccl_comm_init).  The units of
+ * the loop nest CalSurfG.f90:1144-1145 are sharded over ranks in contiguous gather blocks, so the reference's
+ * output is the rank-order concatenation of the ranks' outputs.  One call gathers the predicted times of all rows
+ * (in place in the plan's full-length dsurf) and, with want_coo != 0, the COO row blocks of every rank into a
+ * second device buffer -- the full (rw, iw, col) that main.f90:355-359 receives.  ncclAllGather of the counts, then
+ * grouped ncclBroadcast of each block straight to its offset. */
+int dsurf_plan_allgather(dsurf_plan *plan, void *nccl_comm, int rank, int nranks, int want_coo, int64_t *nar_total);
+double dsurf_plan_last_gather_ms(const dsurf_plan *plan);
+int dsurf_plan_download_gathered(dsurf_plan *plan, int *iw_rows, float *rw, int *col);
+/* order-sensitive 64-bit digest of the plan's own COO (gathered == 0) or of the gathered one: equal digests on
+ * 1 and on N GPUs <=> identical triplets in identical order */
+int dsurf_plan_digest(dsurf_plan *plan, int gathered, uint64_t *digest, int64_t *n);
+
 /* Device-resident LSMR: build from host COO once, then run iterations with everything in HBM. */
 typedef struct dsurf_lsmr_sys dsurf_lsmr_sys;
 int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar, const int *rows1,
@@ -227,6 +240,11 @@ int dsurf_lsmr_create(dsurf_lsmr_sys **sys, int m, int n, int64_t nar, const int
  * place, as the reference's main program does. */
 int dsurf_lsmr_create_from_plan(dsurf_lsmr_sys **sys, dsurf_plan *plan, const float *obst,
                                 float threshold0, float weight);
+/* row-partitioned variant for the distributed LSMR: this rank's system holds the data rows its plan produced
+ * (renumbered from 1) and a contiguous share of the smoothing rows; every rank must hold the predicted times of
+ * all rows (dsurf_plan_allgather).  nranks == 1 is dsurf_lsmr_create_from_plan. */
+int dsurf_lsmr_create_from_plan_shard(dsurf_lsmr_sys **sys, dsurf_plan *plan, const float *obst, float threshold0,
+                                      float weight, int rank, int nranks, int *m_local, int64_t *nnz_local);
 /* results of the last dsurf_lsmr_create_from_plan (any pointer may be NULL): cbst(1:dall) after
  * outlier rejection, datweight(1:dall), stats4 = {q25, q75, maxnorm, averdws} (main.f90:364,386-394),
  * m = dall + count3, nar including the smoothing rows */

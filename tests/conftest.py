@@ -22,6 +22,16 @@ def has_gpu():
         return False
 
 
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a machine without a B200 skips the GPU tests instead of failing them."""
+    if has_gpu():
+        return
+    skip = pytest.mark.skip(reason="needs a B200 (no CUDA device visible)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def taipei():
     from dsurftomo_b200 import inputs

@@ -26,6 +26,25 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTED_SYMBOLS) <= set(syms) | {"dsurf_fatal_"}
 
 
+def test_build_info_carries_the_hash_of_the_sources_in_the_tree():
+    """A stale libdsurf_b200.so (built from other sources than the tree's) is detectable: the Makefile bakes the sha1
+    of every library source into dsurf_build_info()."""
+    import glob
+    import hashlib
+
+    csrc = os.path.join(ROOT, "dsurftomo_b200", "csrc")
+    files = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) +
+                   glob.glob(os.path.join(csrc, "*.cpp")), key=os.path.basename)
+    files = [f for f in files if os.path.basename(f) != "build_info.h"]
+    # GNU make's $(sort ...) orders the words as written in the Makefile: relative names, then ../../include, Makefile
+    names = sorted([os.path.basename(f) for f in files] + ["../../include/dsurftomo_b200.h", "Makefile"])
+    h = hashlib.sha1()
+    for n in names:
+        h.update(open(os.path.join(csrc, n), "rb").read())
+    info = _lib.lib().dsurf_build_info().decode()
+    assert info.endswith("src " + h.hexdigest()[:16]), (info, h.hexdigest()[:16])
+
+
 def test_gfortran_mangled_dropins_present():
     L = _lib.lib()
     for s in ("calsurfg_", "depthkernel_", "caldespersion_", "surfdisp96_", "aprod_", "__lsmrmodule_MOD_lsmr"):
