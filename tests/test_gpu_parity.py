@@ -2,6 +2,8 @@
 on identical inputs.  Bit-exact where the arithmetic is fp32 in reference order (velocity dicing,
 travel times, ray cells / Frechet sums, column patterns); tolerance-checked where the reference
 itself is only defined up to libm / summation order (fp64 root search, LSMR)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -58,23 +60,43 @@ def test_surfdisp96_single_and_higher_mode():
         np.testing.assert_allclose(got, ref, rtol=3e-7, atol=0)
 
 
+def _ulp32(x):
+    """Spacing of REAL*4 numbers at |x| (the reference rounds every dispersion value to REAL*4, surfdisp96.f:292-297)."""
+    return np.spacing(np.abs(x).astype(np.float32)).astype(np.float64)
+
+
 def test_depthkernel_matches_oracle(small_problem):
+    """Phase velocities may differ from the oracle by one REAL*4 ulp in a few per cent of the values (CUDA's and
+    glibc's fp64 sin/cos/exp differ in the last bit, which occasionally moves the REAL*4 rounding of a root).  The
+    finite-difference kernels (c+ - c-)/(0.01 p) (CalSurfG.f90:76-160) inherit exactly that: every kernel entry must
+    equal the oracle's up to a whole number of ulp flips of its two dispersion values (<= 2 ulps in total), and only
+    a few per cent of the entries may differ at all.  Group velocities are a REAL*4 difference quotient over a 1 %
+    period step (surfdisp96.f:281-300): one ulp of a root moves U by ~200 ulps, so they are budgeted in ulps of U."""
     pb = small_problem
     t = np.array([0.6, 1.0, 1.6])
-    for iwave, igr in ((2, 0), (1, 0), (2, 1)):
+    nz = pb.nz
+    vs = pb.vsf.reshape(nz, -1).astype(np.float64)                       # [nz][ncol]
+    vp = 0.9409 + 2.0947 * vs - 0.8206 * vs ** 2 + 0.2683 * vs ** 3 - 0.0251 * vs ** 4   # Brocher (CalSurfG.f90:49-53)
+    rho = 1.6612 * vp - 0.4721 * vp ** 2 + 0.0671 * vp ** 3 - 0.0043 * vp ** 4 + 0.000106 * vp ** 5
+    for iwave, igr in ((2, 0), (1, 0), (2, 1), (1, 1)):
         pv, svs, svp, srho = api.depthkernel(pb.nx, pb.ny, pb.nz, pb.vsf, iwave, igr, len(t), t, pb.depz, pb.minthk)
         rpv, rvs, rvp, rrho = O.depthkernel(pb.vsf, iwave, igr, t, pb.depz, pb.minthk, nthreads=8)
-        rel = np.abs(pv - rpv) / np.abs(rpv)
-        assert rel.max() <= (2e-7 if igr == 0 else 2e-4)
-        # FD kernels amplify 1-ulp differences of c by ~1/(0.01*v*ulp): compare against the kernel scale
-        for a, b in ((svs, rvs), (svp, rvp), (srho, rrho)):
-            scale = np.abs(b).max()
-            assert np.abs(a - b).max() <= (2e-3 if igr == 0 else 5e-2) * scale
+        d_ulps = np.abs(pv - rpv) / _ulp32(rpv)
+        if igr == 0:
+            assert d_ulps.max() <= 1.0 and (d_ulps > 0).mean() <= 0.03, (d_ulps.max(), (d_ulps > 0).mean())
+        else:
+            assert d_ulps.max() <= 600 and np.median(d_ulps) <= 8, (d_ulps.max(), np.median(d_ulps))
+        ulp_c = _ulp32(rpv)[None, :, :]                                   # [1][k][ncol]
+        budget = (2.0 if igr == 0 else 1200.0)
+        for a, b, par in ((svs, rvs, vs), (svp, rvp, vp), (srho, rrho, rho)):
+            flips = np.abs(a - b) * (0.01 * par[:, None, :]) / ulp_c      # difference in ulps of the dispersion values
+            assert flips.max() <= budget * 1.001, (iwave, igr, flips.max())
             if igr == 0:
-                assert (a != b).mean() < 0.05
+                assert (flips > 0).mean() <= 0.06, (flips > 0).mean()
+                assert np.abs(flips - np.round(flips)).max() <= 0.02     # whole ulp flips, nothing else
     pv2 = api.caldespersion(pb.nx, pb.ny, pb.nz, pb.vsf, 2, 0, len(t), t, pb.depz, pb.minthk)
     rpv2 = O.caldespersion(pb.vsf, 2, 0, t, pb.depz, pb.minthk, nthreads=8)
-    assert (np.abs(pv2 - rpv2) / rpv2).max() <= 2e-7
+    assert (np.abs(pv2 - rpv2) / _ulp32(rpv2)).max() <= 1.0
 
 
 # ------------------------------------------------------------------ K2-K5 eikonal + rays
@@ -230,22 +252,59 @@ def test_lsmr_random_system_vs_dense():
     assert np.abs(got2["x"] - xs).max() <= 2e-4 * np.abs(xs).max()
 
 
-def test_outer_iteration_model_update(taipei):
-    """One full outer iteration (CalSurfG -> glue -> LSMR -> update) against the oracle chain."""
-    pb = taipei
+def _outer_iteration_vs_oracle(pb, nthreads=8):
+    """One full outer iteration (main.f90:348-546 without the file output): CalSurfG -> residuals, outlier weights,
+    smoothing rows -> LSMR -> model update, on the GPU through the C ABI and on the oracle chain."""
     got = api.CalSurfG(pb)
     s = hostglue.host_glue(pb, got["dsurf"], got["row"], got["col"], got["rw"])
     iw = hostglue.pack_iw(s["rows"], s["cols"])
     sol = api.LSMR(s["m"], s["n"], len(iw), len(s["vals"]), iw, s["vals"], s["cbst"], pb.damp, 1e-6, 1e-6, 100.0,
                    400, 10)
     vs_new, _ = hostglue.model_update(pb, pb.vsf, sol["x"])
-    ref = O.calsurfg(pb, nthreads=8, mode=1)
+    ref = O.calsurfg(pb, nthreads=nthreads, mode=1)
+    assert ref["err"] == 0
     iwr, rwr, colr = ref["iw"].copy(), ref["rw_full"].copy(), ref["col_full"].copy()
     m, nar, cbst, _ = O.host_glue(pb, ref["dsurf"], iwr, rwr, colr, ref["nar"])
     L = O.lsmr(m, pb.maxvp, iwr[: 2 * nar + 1], rwr[:nar], cbst[:m], pb.damp)
     vs_ref, _ = O.model_update(pb, pb.vsf, L["x"])
     assert m == s["m"]
-    assert np.abs(vs_new / vs_ref - 1).max() <= 1e-5
+    a = set(zip(got["row"].tolist(), got["col"].tolist()))
+    b = set(zip(ref["row"].tolist(), ref["col"].tolist()))
+    return dict(got=got, ref=ref, vs_new=vs_new, vs_ref=vs_ref, itn=(sol["itn"], L["itn"]),
+                pattern_mismatch=len(a ^ b), pattern_total=len(b),
+                dsurf_rel=float(np.abs(got["dsurf"] / ref["dsurf"] - 1).max()),
+                vs_rel=float(np.abs(vs_new / vs_ref - 1).max()))
+
+
+def test_outer_iteration_model_update(taipei):
+    """Taipei (Rayleigh phase): Vs model after one outer iteration within 1e-5 relative (north_star)."""
+    r = _outer_iteration_vs_oracle(taipei)
+    assert r["vs_rel"] <= 1e-5, r["vs_rel"]
+
+
+def test_outer_iteration_all_four_data_types(small_problem):
+    """Rayleigh + Love, phase + group (Rc, Rg, Lc, Lg) through CalSurfG -> glue -> LSMR -> update: the north_star
+    tolerances hold for every data type, not only for Rayleigh phase.  Pattern mismatches (entries whose |row| sits
+    within an ulp of the 1e-4 threshold, CalSurfG.f90:1425) are counted, not assumed zero."""
+    r = _outer_iteration_vs_oracle(small_problem)
+    print("4 types:", {k: r[k] for k in ("dsurf_rel", "vs_rel", "pattern_mismatch", "pattern_total", "itn")})
+    assert r["dsurf_rel"] <= 1e-5
+    assert r["pattern_mismatch"] <= 2e-4 * r["pattern_total"], (r["pattern_mismatch"], r["pattern_total"])
+    assert abs(r["itn"][0] - r["itn"][1]) <= 2
+    assert r["vs_rel"] <= 1e-5, r["vs_rel"]
+
+
+def test_cfg2_whole_configuration_vs_oracle():
+    """BASELINE configs[1] run whole (257 x 257 propagation grid, 8 periods x 64 sources, Rayleigh phase, 512 sweeps,
+    8192 rays): predicted times within 1e-5 relative, sparsity-pattern mismatches counted, and the Vs model after one
+    outer iteration within 1e-5 relative."""
+    pb = inputs.config(2)
+    r = _outer_iteration_vs_oracle(pb, nthreads=os.cpu_count() or 8)
+    print("cfg 2:", {k: r[k] for k in ("dsurf_rel", "vs_rel", "pattern_mismatch", "pattern_total", "itn")})
+    assert r["dsurf_rel"] <= 1e-5
+    assert r["pattern_mismatch"] <= 2e-4 * r["pattern_total"], (r["pattern_mismatch"], r["pattern_total"])
+    assert abs(r["itn"][0] - r["itn"][1]) <= 2
+    assert r["vs_rel"] <= 1e-5, r["vs_rel"]
 
 
 def test_synthetic_matches_oracle(taipei, tmp_path):
