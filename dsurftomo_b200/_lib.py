@@ -94,6 +94,7 @@ EXPORTED_SYMBOLS = [
     "dsurf_plan_debug_sweep", "dsurf_plan_get_dispersion", "dsurf_plan_timings", "dsurf_plan_last_sweeps_ms",
     "dsurf_plan_glue_results", "dsurf_plan_update_model",
     "dsurf_lsmr_create", "dsurf_lsmr_create_from_plan", "dsurf_lsmr_hint_geometry", "dsurf_lsmr_destroy", "dsurf_lsmr_set_comm",
+    "dsurf_lsmr_xchg_export", "dsurf_lsmr_xchg_attach",
     "dsurf_lsmr_solve", "dsurf_lsmr_nnz", "dsurf_nccl_unique_id", "dsurf_nccl_comm_init",
     "dsurf_nccl_comm_destroy",
 ]

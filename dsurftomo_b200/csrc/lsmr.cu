@@ -1070,6 +1070,90 @@ __global__ void k_sumsq(const float *x, long long n, double *partial) {
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 // dist: reduce partials into one device double (then all-reduced by NCCL)
+// ---------------------------------------------------------------------------------------------
+// One-shot exchange of the distributed LSMR over peer memory (NVLink / NVSwitch), replacing the
+// per-iteration ncclAllReduce: rows of A are partitioned over ranks, so every iteration needs the sum
+// over ranks of the partial A'u (n floats) and of the partial ||u||^2 (one double) --
+// lsmrModule.f90:486-497 with aprod.f90:40-55 split by rows.  Every rank owns an exchange buffer that all
+// peers have mapped (CUDA IPC):  [slot 0 | slot 1 | arrival flags | epoch],  slot = n floats + 1 double.
+//   k_xchg_signal   after the local A'u has been written into this rank's slot (epoch parity): bump the local
+//                   epoch and store it into flag[rank] of EVERY rank's buffer (system-scope release);
+//   k_xchg_reduce   wait until all flags of the local buffer reached the epoch (acquire), then every rank adds
+//                   the same n-vectors in the same order rank 0..N-1 -- reading each peer's slot straight over
+//                   NVLink -- so the replicated vectors stay bit-identical on all ranks; fused with the update
+//                   v = -beta v + (1/beta) A'u of :495-497 needs beta, hence the separate k_fused_beta between.
+// Two slots: a rank can run at most one iteration ahead of its slowest peer (it needs that peer's flag of the
+// intermediate iteration), so slot parity never collides.  No NCCL call, no host interaction: the whole
+// iteration (two of them, one per parity) is a CUDA graph.  A watchdog turns a missing peer into an error
+// instead of a hang.
+struct XchgHdr {
+  int flag[64];
+  int epoch;
+  int error;
+};
+__host__ __device__ __forceinline__ XchgHdr *xchg_hdr(char *buf, size_t stride) { return reinterpret_cast<XchgHdr *>(buf + 2 * stride); }
+
+__global__ void k_xchg_signal(const LsmrScalars *S, char *const *peers, int rank, int nranks, size_t stride,
+                              const double *part, int np) {
+  if (S->stop) return;
+  char *mine = peers[rank];
+  XchgHdr *h = xchg_hdr(mine, stride);
+  const double usum = block_reduce_partials(part, np);  // local ||u||^2, same fixed order as everywhere
+  __shared__ int ep;
+  if (threadIdx.x == 0) {
+    ep = h->epoch + 1;
+    h->epoch = ep;
+    *reinterpret_cast<double *>(mine + (size_t)(ep & 1) * stride + stride - sizeof(double)) = usum;
+    __threadfence_system();  // the slot (written by the product kernel before this one, and usum) before the flags
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nranks) {
+    volatile int *f = &xchg_hdr(peers[threadIdx.x], stride)->flag[rank];
+    *f = ep;
+  }
+}
+
+__global__ void k_xchg_reduce(LsmrScalars *S, char *const *peers, int rank, int nranks, size_t stride, int n,
+                              float *vsum, double *usum_out) {
+  if (S->stop) return;
+  XchgHdr *h = xchg_hdr(peers[rank], stride);
+  __shared__ int ep;
+  if (threadIdx.x == 0) {
+    const int e = h->epoch;
+    const long long t0 = clock64();
+    bool ok = true;
+    for (int r = 0; r < nranks && ok; r++) {
+      volatile int *f = &h->flag[r];
+      while (*f < e) {
+        if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer is gone
+          ok = false;
+          break;
+        }
+      }
+    }
+    if (!ok) h->error = 1;
+    __threadfence_system();
+    ep = ok ? e : -1;
+  }
+  __syncthreads();
+  if (ep < 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) S->stop = 1;  // the host reports DSURF_ERR_NCCL (exchange timed out)
+    return;
+  }
+  const size_t off = (size_t)(ep & 1) * stride;
+  const long long tot = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += tot) {
+    float acc = 0.0f;
+    for (int r = 0; r < nranks; r++) acc += __ldcv(reinterpret_cast<const float *>(peers[r] + off) + i);
+    vsum[i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double u = 0.0;
+    for (int r = 0; r < nranks; r++) u += __ldcv(reinterpret_cast<const double *>(peers[r] + off + stride - sizeof(double)));
+    *usum_out = u;
+  }
+}
+
 __global__ void k_reduce_to(double *out, const double *partial, int np) {
   const double s = block_reduce_partials(partial, np);
   if (threadIdx.x == 0) *out = s;
@@ -1285,6 +1369,11 @@ struct dsurf_lsmr_sys {
   int rank = 0, nranks = 1;
   DevBuf<float> vpart;
   DevBuf<double> red;
+  // one-shot exchange over peer memory (NVLink): see k_xchg_signal / k_xchg_reduce
+  char *xbuf = nullptr;             // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
+  size_t xstride = 0, xbytes = 0;   // bytes of one parity slot / of the whole buffer
+  DevBuf<char *> xpeers;            // device table: exchange buffers of every rank (this rank's own at [rank])
+  bool xready = false;
   bool solved = false;
   // fused small-vector phases (k_fused_beta / k_fused_tail): cluster size (0 = unfused path),
   // elements of the n-vectors per CTA, dynamic shared memory of the tail kernel
@@ -1297,6 +1386,7 @@ struct dsurf_lsmr_sys {
     if (evj) cudaEventDestroy(evj);
     if (st2) cudaStreamDestroy(st2);
     if (own_stream && st) cudaStreamDestroy(st);
+    if (xbuf) cudaFree(xbuf);
   }
 };
 
@@ -1557,6 +1647,43 @@ extern "C" int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *comm, int rank, in
   return DSURF_OK;
 }
 
+// ---- peer-memory exchange set-up (see k_xchg_signal): export this rank's buffer, then map everybody's
+extern "C" int dsurf_lsmr_xchg_export(dsurf_lsmr_sys *s, void *handle64) {
+  if (!s || !handle64) return DSURF_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!s->xbuf) {
+    s->xstride = (((size_t)s->n_int * sizeof(float) + sizeof(double)) + 255) & ~(size_t)255;
+    s->xbytes = 2 * s->xstride + sizeof(XchgHdr);
+    DS_CUDA(cudaMalloc(&s->xbuf, s->xbytes));
+    DS_CUDA(cudaMemset(s->xbuf, 0, s->xbytes));
+  }
+  cudaIpcMemHandle_t h;
+  DS_CUDA(cudaIpcGetMemHandle(&h, s->xbuf));
+  memcpy(handle64, &h, 64);
+  return DSURF_OK;
+}
+extern "C" int dsurf_lsmr_xchg_attach(dsurf_lsmr_sys *s, const void *handles, int rank, int nranks) {
+  if (!s || !handles || !s->xbuf || rank < 0 || rank >= nranks || nranks > 64) return DSURF_ERR_BAD_ARG;
+  std::vector<char *> tab(nranks, nullptr);
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) {
+      tab[r] = s->xbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+    void *ptr = nullptr;
+    DS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    tab[r] = (char *)ptr;
+  }
+  if (s->xpeers.reserve(nranks)) return DSURF_ERR_CUDA;
+  DS_CUDA(cudaMemcpy(s->xpeers.p, tab.data(), nranks * sizeof(char *), cudaMemcpyHostToDevice));
+  s->rank = rank;
+  s->nranks = nranks;
+  s->xready = getenv("DSURF_LSMR_NCCL_ONLY") == nullptr;
+  return DSURF_OK;
+}
+
 // Chooses the cluster size of the fused small-vector kernels: the largest of 16 (non-portable) / 8
 // whose per-CTA slice of v fits in shared memory and that the device can co-schedule; 0 = unfused.
 static void choose_fused(dsurf_lsmr_sys *s) {
@@ -1618,7 +1745,7 @@ static cudaError_t launch_cluster(void (*kern)(KArgs...), int cl, size_t smem, c
 
 // one LSMR iteration's kernel sequence (lsmrModule.f90:475-616) on stream st
 static int enqueue_iteration(dsurf_lsmr_sys *s, float damp, float atol, float btol, float ctol, int itnlim,
-                             int force_iters, int localVecs, bool dist) {
+                             int force_iters, int localVecs, bool dist, int parity = 0) {
   cudaStream_t st = s->st;
   const int m = s->m, n = s->n_int;  // n-vectors in the internal layout
   LsmrScalars *S = s->S.p;
@@ -1638,6 +1765,20 @@ static int enqueue_iteration(dsurf_lsmr_sys *s, float damp, float atol, float bt
     }
     // v = A'u - beta v (:495-497)
     launch_product(st, s->At, s->u.p, s->v.p, &S->neg_beta, 1.0f, nullptr, &S->stop, s);
+  } else if (s->xready) {
+    // peer-memory exchange: local A'u straight into this rank's slot, signal, wait + sum over ranks
+    float *slot = reinterpret_cast<float *>(s->xbuf + (size_t)parity * s->xstride);
+    launch_product(st, s->At, s->u.p, slot, nullptr, 0.0f, nullptr, &S->stop, nullptr);
+    k_xchg_signal<<<1, 1024, 0, st>>>(S, s->xpeers.p, s->rank, s->nranks, s->xstride, part, s->A.blocks());
+    k_xchg_reduce<<<gvec, 256, 0, st>>>(S, s->xpeers.p, s->rank, s->nranks, s->xstride, n, s->vpart.p, s->red.p);
+    if (cl > 0) {
+      DS_CUDA(launch_cluster(k_fused_beta, cl, 0, st, S, (const double *)part, s->A.blocks(), (const double *)s->red.p,
+                             localVecs, s->u.p, m, (const float *)s->v.p, s->localV.p, n));
+    } else {
+      k_beta<<<1, 1024, 0, st>>>(S, part, s->A.blocks(), s->red.p, localVecs);
+      k_scale_u_enqueue<<<gvecm, 256, 0, st>>>(S, s->u.p, m, s->v.p, s->localV.p, n, localVecs > 0 ? 1 : 0);
+    }
+    k_combine_v<<<gvec, 256, 0, st>>>(S, s->v.p, s->vpart.p, n);
   } else {
     // one fused exchange per iteration: partial A'u_raw (n floats) + partial ||u||^2 (1 double)
     k_reduce_to<<<1, 1024, 0, st>>>(s->red.p, part, s->A.blocks());
@@ -1736,10 +1877,19 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
   // every kPoll iterations (the solution is frozen at the exact stopping iteration).
   cudaGraph_t &graph = guard.graph;
   cudaGraphExec_t &gexec = guard.gexec;
-  const bool use_graph = !dist && getenv("DSURF_LSMR_NO_GRAPH") == nullptr;
+  const bool xchg = dist && s->xready;
+  int par0 = 0;  // slot parity of the next iteration = parity of (epoch + 1), identical on every rank
+  if (xchg) {
+    int e0 = 0;
+    DS_CUDA(cudaMemcpy(&e0, &xchg_hdr(s->xbuf, s->xstride)->epoch, sizeof(int), cudaMemcpyDeviceToHost));
+    par0 = (e0 + 1) & 1;
+  }
+  const bool use_graph = (!dist || xchg) && getenv("DSURF_LSMR_NO_GRAPH") == nullptr;
   if (use_graph && !h_stop) {
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      int rc = enqueue_iteration(s, damp, atol, btol, ctol, itnlim, force_iters, localVecs, false);
+      int rc = enqueue_iteration(s, damp, atol, btol, ctol, itnlim, force_iters, localVecs, dist, par0);
+      if (xchg && rc == DSURF_OK)  // the exchange alternates between two slots: one graph = two iterations
+        rc = enqueue_iteration(s, damp, atol, btol, ctol, itnlim, force_iters, localVecs, dist, par0 ^ 1);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
       if (rc != DSURF_OK || ce != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
         if (graph) cudaGraphDestroy(graph);
@@ -1758,7 +1908,7 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
       if (gexec) {
         DS_CUDA(cudaGraphLaunch(gexec, st));
       } else {
-        DS_CHECK(enqueue_iteration(s, damp, atol, btol, ctol, itnlim, force_iters, localVecs, dist));
+        DS_CHECK(enqueue_iteration(s, damp, atol, btol, ctol, itnlim, force_iters, localVecs, dist, (par0 + launched) & 1));
       }
       launched++;
     }
@@ -1767,6 +1917,15 @@ extern "C" int dsurf_lsmr_solve(dsurf_lsmr_sys *s, float damp, float atol, float
     if (launched > itnlim + 8) break;
   }
   cudaEventRecord(e1, st);
+  if (xchg) {
+    int xerr = 0;
+    DS_CUDA(cudaMemcpyAsync(&xerr, &xchg_hdr(s->xbuf, s->xstride)->error, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    if (xerr) {
+      set_error(__FILE__, __LINE__, "distributed LSMR: a peer never signalled its partial A'u (peer-memory exchange timed out)");
+      return DSURF_ERR_NCCL;
+    }
+  }
   LsmrScalars hs;
   DS_CUDA(cudaMemcpyAsync(&hs, S, sizeof(hs), cudaMemcpyDeviceToHost, st));
   // x in the reference's column order k*P + pos stays in xout (read by the device-side model update)

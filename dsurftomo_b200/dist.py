@@ -89,9 +89,31 @@ class NcclComm:
             self.h = None
 
 
-def attach(lsmr_system, comm: NcclComm):
+def attach(lsmr_system, comm: NcclComm, peer_exchange: bool = True, device=None):
+    """Binds a row-partitioned LSMR system to the communicator.  With peer_exchange (default) the per-iteration
+    all-reduce runs over peer-mapped exchange buffers (attach_peer_exchange); DSURF_LSMR_NCCL_ONLY=1 keeps NCCL."""
     check(lib().dsurf_lsmr_set_comm(lsmr_system.h, comm.h, C.c_int(comm.rank), C.c_int(comm.world)),
           "lsmr_set_comm")
+    if peer_exchange and comm.world > 1:
+        attach_peer_exchange(lsmr_system, comm, device)
+
+
+def attach_peer_exchange(lsmr_system, comm: NcclComm, device=None):
+    """Maps every rank's LSMR exchange buffer into every other rank (CUDA IPC over NVLink): the per-iteration
+    all-reduce becomes direct peer loads inside a CUDA graph.  Call after attach()."""
+    import torch
+    import torch.distributed as dist
+
+    hb = (C.c_char * 64)()
+    check(lib().dsurf_lsmr_xchg_export(lsmr_system.h, hb), "lsmr_xchg_export")
+    mine = torch.frombuffer(bytearray(bytes(hb)), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        mine = mine.cuda(device)
+    allh = [torch.empty_like(mine) for _ in range(comm.world)]
+    dist.all_gather(allh, mine)
+    raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+    check(lib().dsurf_lsmr_xchg_attach(lsmr_system.h, C.c_char_p(raw), C.c_int(comm.rank), C.c_int(comm.world)),
+          "lsmr_xchg_attach")
 
 
 def partition_system(sysd: dict, rank: int, world: int):

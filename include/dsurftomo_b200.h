@@ -262,6 +262,12 @@ int dsurf_lsmr_destroy(dsurf_lsmr_sys *sys);
 /* multi-GPU: rows are partitioned over ranks; comm is an ncclComm_t created by the host side
  * (see dsurftomo_b200/dist.py); the per-iteration exchange is one all-reduce of n+1 floats. */
 int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *nccl_comm, int rank, int nranks);
+/* peer-memory exchange of the distributed LSMR (replaces the per-iteration NCCL all-reduce by direct NVLink loads
+ * from every rank's exchange buffer; the iteration becomes a CUDA graph): every rank exports the CUDA IPC handle of
+ * its buffer (64 bytes), the host side all-gathers the handles (dsurftomo_b200/dist.py) and attaches them.
+ * dsurf_lsmr_set_comm is still needed (the two set-up reductions of a solve use NCCL). */
+int dsurf_lsmr_xchg_export(dsurf_lsmr_sys *sys, void *handle64);
+int dsurf_lsmr_xchg_attach(dsurf_lsmr_sys *sys, const void *handles /* nranks x 64 bytes */, int rank, int nranks);
 int dsurf_nccl_unique_id(void *id128);
 int dsurf_nccl_comm_init(void **comm, const void *id128, int rank, int nranks);
 int dsurf_nccl_comm_destroy(void *comm);
