@@ -86,7 +86,7 @@ EXPORTED_SYMBOLS = [
     # gfortran-convention drop-ins
     "calsurfg_", "depthkernel_", "caldespersion_", "surfdisp96_", "__lsmrmodule_MOD_lsmr", "aprod_", "synthetic_",
     # neutral C API
-    "dsurf_last_error", "dsurf_set_device", "dsurf_build_info", "dsurf_calsurfg", "dsurf_synthetic", "dsurf_depthkernel",
+    "dsurf_last_error", "dsurf_set_device", "dsurf_build_info", "dsurf_set_eikonal_mode", "dsurf_get_eikonal_mode", "dsurf_calsurfg", "dsurf_synthetic", "dsurf_depthkernel",
     "dsurf_surfdisp96", "dsurf_surfdisp96_batch", "dsurf_lsmr", "dsurf_aprod",
     "dsurf_plan_create", "dsurf_plan_create_forward", "dsurf_plan_destroy", "dsurf_plan_set_model", "dsurf_plan_dispersion",
     "dsurf_plan_set_map", "dsurf_plan_set_dispersion", "dsurf_plan_finalize_dispersion", "dsurf_plan_reset_rows", "dsurf_plan_sweeps", "dsurf_plan_num_gathers",

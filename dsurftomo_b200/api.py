@@ -30,6 +30,20 @@ F32, F64, I32 = np.float32, np.float64, np.int32
 _dummy64 = np.zeros(1, F64)
 
 
+EIKONAL_MODES = {"exact": 0, "lps": 1, "fim": 2}
+
+
+def set_eikonal_mode(mode):
+    """Eikonal pipeline of plans / CalSurfG calls created after this call (dsurf_set_eikonal_mode):
+    "exact" (default: the reference's heap pop order, bit-identical times), "lps" (exact, lane per sweep) or
+    "fim" (block-level fast-iterative sweep, last-bit deviations where the reference's heap leaves time order).
+    Returns the previous mode name."""
+    prev = lib().dsurf_get_eikonal_mode()
+    m = EIKONAL_MODES[mode] if isinstance(mode, str) else int(mode)
+    check(lib().dsurf_set_eikonal_mode(C.c_int(m)), "set_eikonal_mode")
+    return [k for k, v in EIKONAL_MODES.items() if v == prev][0]
+
+
 def _c(a, dt):
     return np.ascontiguousarray(a, dt)
 

@@ -26,6 +26,8 @@
 #include "common.cuh"
 #include "plan.cuh"
 #include "eik_lps.cuh"
+#include "eik_fim.cuh"
+#include <cstring>
 
 namespace dsurf {
 
@@ -786,7 +788,7 @@ constexpr int kBoxMax = (2 * kSgs + 1) * (2 * kSgs + 1);  // 289 coarse nodes in
 
 template <int kG>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, V3<kG>::MINB)
-k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ velv_all, BatchView bv) {
+k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ velv_all, BatchView bv, bool write_words) {
   extern __shared__ float smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kNG = V3<kG>::NG, kHS3 = V3<kG>::HS;
@@ -803,8 +805,8 @@ k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ 
   SweepDesc d = sw[slot];
   const size_t Nc = (size_t)g.nnx * g.nnz;
   const float *velv = velv_all + (size_t)d.map * g.nx * g.ny;
-  const int wld = g.nnz + 2 * lps::kPad;  // padded word array (eik_lps.cuh)
-  unsigned *word = bv.word + (size_t)slot * ((size_t)(g.nnx + 2 * lps::kPad) * wld);
+  const int wld = bv.wld;  // padded word array (eik_lps.cuh)
+  unsigned *word = bv.word + (size_t)slot * bv.wslot;
   int2 *noder = bv.noder + (size_t)slot * kRefMax * kRefMax;
   float *velr = bv.velr + (size_t)slot * kRefMax * kRefMax;
   int2 *box = bv.box + (size_t)slot * kBoxMax;
@@ -840,13 +842,14 @@ k_refine(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ 
     }
   }
   __syncwarp(gm);
+  if (!write_words) return;  // fast-iterative pipeline: k_fim_start picks the box up from here
   int ns = 0;
   for (int cx = 0; cx < bw; cx++) {
     for (int base = 0; base < bh; base += kG) {
       const int cz = base + gl;
       int2 v = make_int2(0, -1);
       if (cz < bh) v = box[cx * bh + cz];
-      const int xi = (d.vnl - 1 + cx + lps::kPad) * wld + (d.vnt - 1 + cz + lps::kPad);  // padded node id
+      const int xi = (d.vnl - 1 + cx + bv.wpx) * wld + (d.vnt - 1 + cz + bv.wpz);  // padded node id
       const bool close = (v.y > 0 || v.y == -100);
       if (cz < bh && v.y == 0) word[xi] = (unsigned)v.x;
       const unsigned mask = (__ballot_sync(gm, close) >> gbase) & ((1u << kG) - 1u);
@@ -1022,25 +1025,314 @@ k_march_lps(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict
   }
 }
 
-// Pipeline selection.  Default: the single-kernel march with 16 lanes per sweep (k_eikonal3).  DSURF_EIKONAL_LPS=1
-// selects k_refine + k_march_lps (lane per sweep, warp-specialised).  Measured on B200 at cfg 3 (profiles/
-// r02_eikonal_lps.md): 33 s per stage against 22.6 s -- with one lane per sweep every load touches 32 distinct lines
-// and the slowest of 32 unrelated sweeps sets the pace of each acceptance, so the time per acceptance grows from
-// 8.6 us (1 K sweeps resident) to 27.5 us (24.6 K); it needs 2.4x fewer DRAM bytes and 5x fewer issue slots per
-// accepted node, but the machine is latency-, not throughput-bound on this path.
-static bool legacy_v3() {
-  static const bool v = getenv("DSURF_EIKONAL_LPS") == nullptr;
-  return v;
+// =============================================================================================
+// Fast-iterative pipeline (DSURF_EIKONAL=fim): k_refine (exact, as above) -> k_fim_start (exact start-up of the
+// coarse pass, one thread per sweep) -> k_fim_march (block-level fast-iterative sweep, one CTA per sweep, one warp per
+// 32 x 32 tile).  Algorithm, its relation to the reference's heap march and the measured deviations: eik_fim.cuh.
+// =============================================================================================
+constexpr int kFimWarps = 8;
+
+__global__ void __launch_bounds__(128)
+k_fim_start(Geom g, const SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
+            const float *__restrict__ risti_c, BatchView bv) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nsw) return;
+  const SweepDesc d = sw[slot];
+  fim::StartCtx C;
+  C.nnx = g.nnx;
+  C.nnz = g.nnz;
+  C.rx0 = max(0, d.isx - 1 - fim::kRegHalf);
+  C.rz0 = max(0, d.isz - 1 - fim::kRegHalf);
+  C.rw = min(g.nnx - 1, d.isx + fim::kRegHalf) - C.rx0 + 1;
+  C.rh = min(g.nnz - 1, d.isz + fim::kRegHalf) - C.rz0 + 1;
+  C.ri = g.earth;
+  C.dnx = g.dnx;
+  C.dnz = g.dnz;
+  C.vel = veln_all + (size_t)d.map * ((size_t)g.nnx * g.nnz);
+  C.risti = risti_c;
+  fim::StartMem M;
+  M.w = bv.fim_rw + (size_t)slot * fim::kRegNodes;
+  M.heap = reinterpret_cast<lps::Ent *>(bv.hent + (size_t)slot * bv.slab);  // the refined pass is done with its slab
+  M.flag = bv.fim_flag + (size_t)slot * fim::kRegNodes;
+  int2 *reg = bv.fim_reg + (size_t)slot * fim::kRegNodes;
+  bv.fim_rect[slot] = make_int4(C.rx0, C.rz0, C.rw, C.rh);
+  if (d.status != 0) {  // the refined pass failed: nothing to propagate
+    for (int i = 0; i < C.rw * C.rh; i++) reg[i] = make_int2(0, -1);
+    return;
+  }
+  const int2 *box = bv.box + (size_t)slot * kBoxMax;
+  int ntr = 0;
+  fim::startup_march(C, M, reinterpret_cast<const int *>(box), d.vnl - 1, d.vnt - 1, d.vnr - d.vnl + 1, d.vnb - d.vnt + 1, ntr,
+                     C.rw * C.rh);
+  for (int i = 0; i < C.rw * C.rh; i++) {
+    const unsigned w = M.w[i];
+    int2 r;
+    if (lps::alive(w))
+      r = make_int2((int)w, 0);
+    else if (w == lps::kFar)
+      r = make_int2(0, -1);
+    else
+      r = make_int2(M.heap[w & 0x7FFFFFFFu].x, 1);
+    reg[i] = r;
+  }
 }
-bool eikonal_uses_words() { return !legacy_v3(); }
 
-// bytes of per-sweep heap slab (in int2 entries) the selected pipeline needs for capacity hcap
-int eikonal_slab_entries(int hcap) { return std::max(hcap + 1, legacy_v3() ? 0 : lps_slab_entries(hcap)); }
+struct FimShared {       // per-CTA control block (one CTA = one sweep)
+  int nlist, next, pad0, pad1;
+};
 
-// legacy pipeline: sweeps that can be resident at once (its batches are sized to whole waves);
-// the lane-per-sweep pipeline keeps every sweep of a batch resident and is limited by memory only
-int eikonal_resident_sweeps() {
-  if (!legacy_v3()) return 0;
+// one warp relaxes one tile: load (times + halo, slowness), anti-diagonal walks, store, marks for the neighbours
+__device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fim::Layout L, int tile, unsigned *T,
+                                 unsigned *bitmap, unsigned char *active, const float *vel, const float *risti_c, int srcx,
+                                 int srcz, int lane) {
+  const int tx = tile / L.ntz, tz = tile - tx * L.ntz;
+  unsigned *bm = bitmap + (size_t)tile * fim::kT;
+  const unsigned mydirty = atomicExch(bm + lane, 0u);
+  if (!__any_sync(kFull, mydirty != 0)) return;  // activated by a neighbour whose marks were consumed already
+  fim::TileCtx C = Cb;
+  C.gx0 = tx * fim::kT;
+  C.gz0 = tz * fim::kT;
+  // ---- load: 36 rows of 40 words (16-byte aligned), far -> +inf, region nodes alive before the pass get the flag
+  const bool touches = C.gx0 - fim::kHX < C.bx0 + C.bw && C.gx0 + fim::kT + fim::kHX > C.bx0 &&
+                       C.gz0 - fim::kHZ < C.bz0 + C.bh && C.gz0 + fim::kT + fim::kHZ > C.bz0;
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(T + (size_t)C.gx0 * L.pitch + C.gz0);  // row gx0 - kHX, column gz0 - kHZ
+    constexpr int kVecRow = fim::kPitch / 4;
+    for (int i = lane; i < fim::kRows * kVecRow; i += 32) {
+      const int r = i / kVecRow, c4 = i - r * kVecRow;
+      uint4 v = __ldcg(src + (size_t)r * (L.pitch / 4) + c4);
+      v.x = (int)v.x < 0 ? fim::kInf : v.x;
+      v.y = (int)v.y < 0 ? fim::kInf : v.y;
+      v.z = (int)v.z < 0 ? fim::kInf : v.z;
+      v.w = (int)v.w < 0 ? fim::kInf : v.w;
+      if (touches) {
+        const int bx = C.gx0 + r - fim::kHX - C.bx0, bz = C.gz0 + 4 * c4 - fim::kHZ - C.bz0;
+        if (bx >= 0 && bx < C.bw) {
+          unsigned *e = &v.x;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (bz + k >= 0 && bz + k < C.bh && C.box[2 * (bx * C.bh + bz + k) + 1] == 0) e[k] |= fim::kInit;
+        }
+      }
+      *reinterpret_cast<uint4 *>(tl.t + r * fim::kPitch + 4 * c4) = v;
+    }
+  }
+  {
+    const int gz = C.gz0 + lane;
+    for (int x = 0; x < fim::kT; x++) {
+      const int gx = C.gx0 + x;
+      float sl = 1.0f;
+      if (gx < C.nnx && gz < C.nnz) sl = 1.0f / __ldg(vel + (size_t)gx * C.nnz + gz);
+      tl.slow[x * fim::kT + lane] = sl;
+    }
+    const int gx = C.gx0 + lane;
+    tl.risti[lane] = gx < C.nnx ? __ldg(risti_c + gx) : 0.0f;
+    tl.dirty[lane] = mydirty;
+    if (lane < 4) tl.hx[lane] = 0;
+    if (lane >= 4 && lane < 8) tl.hz[lane - 4] = 0;
+  }
+  __syncwarp();
+  // ---- relax: anti-diagonal walks (lane = tile row), first away from the source
+  const int sx0 = (C.gx0 + fim::kT / 2 >= srcx) ? 1 : -1, sz0 = (C.gz0 + fim::kT / 2 >= srcz) ? 1 : -1;
+  bool changed = false;
+  volatile unsigned *vdirty = tl.dirty;
+  for (int w = 0; w < 32; w++) {
+    if (!__any_sync(kFull, vdirty[lane] != 0)) break;
+    const int sx = (w & 1) ? -sx0 : sx0, sz = (w & 2) ? -sz0 : sz0;
+    for (int dg = 0; dg < 2 * fim::kT - 1; dg++) {
+      const int z = fim::diag_z(lane, dg, sx, sz);
+      const bool mine = z >= 0 && ((vdirty[lane] >> z) & 1u);
+      if (!__any_sync(kFull, mine)) continue;
+      if (mine) changed |= fim::relax_node(tl, C, lane, z);
+      __syncwarp();
+    }
+  }
+  changed = __any_sync(kFull, changed);
+  // ---- store the interior (coalesced rows), then hand the marks to the neighbour tiles
+  if (changed) {
+    const int gz = C.gz0 + lane;
+    for (int x = 0; x < fim::kT; x++) {
+      const int gx = C.gx0 + x;
+      const unsigned w = *tl.at(x, lane);
+      if (gx < C.nnx && gz < C.nnz && (int)w >= 0) T[L.at(gx, gz)] = (w == fim::kInf) ? fim::kFarG : w;
+    }
+  }
+  __threadfence_block();
+  __syncwarp();
+  {
+    // x-neighbours: halo rows -2, -1 are rows 30, 31 of tile (tx - 1, tz); rows 32, 33 are rows 0, 1 of (tx + 1, tz)
+    if (lane < 4) {
+      const unsigned m = tl.hx[lane];
+      const int ntx = lane < 2 ? tx - 1 : tx + 1;
+      if (m && ntx >= 0 && ntx < L.ntx) {
+        const int nt = ntx * L.ntz + tz;
+        atomicOr(bitmap + (size_t)nt * fim::kT + (lane < 2 ? fim::kT - 2 + lane : lane - 2), m);
+        active[nt] = 1;
+      }
+    }
+    // z-neighbours: halo columns -2, -1 are bits 30, 31 of tile (tx, tz - 1); columns 32, 33 are bits 0, 1 of (tx, tz + 1)
+    const unsigned lo = (((tl.hz[0] >> lane) & 1u) << 30) | (((tl.hz[1] >> lane) & 1u) << 31);
+    const unsigned hi = ((tl.hz[2] >> lane) & 1u) | (((tl.hz[3] >> lane) & 1u) << 1);
+    if (lo && tz - 1 >= 0) {
+      atomicOr(bitmap + (size_t)(tile - 1) * fim::kT + lane, lo);
+      active[tile - 1] = 1;
+    }
+    if (hi && tz + 1 < L.ntz) {
+      atomicOr(bitmap + (size_t)(tile + 1) * fim::kT + lane, hi);
+      active[tile + 1] = 1;
+    }
+    const unsigned left = vdirty[lane];  // walk limit reached: the tile stays active
+    if (left) {
+      atomicOr(bm + lane, left);
+      active[tile] = 1;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kFimWarps * 32, 2)
+k_fim_march(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all, const float *__restrict__ risti_c,
+            BatchView bv, fim::Layout L) {
+  extern __shared__ uint4 fsm4[];
+  fim::Tile *tiles = reinterpret_cast<fim::Tile *>(fsm4);
+  FimShared *ctl = reinterpret_cast<FimShared *>(tiles + kFimWarps);
+  const int ntiles = L.ntx * L.ntz;
+  unsigned short *list = reinterpret_cast<unsigned short *>(ctl + 1);
+  unsigned char *active = reinterpret_cast<unsigned char *>(list + ((ntiles + 7) & ~7));
+  const int slot = blockIdx.x;
+  const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SweepDesc d = sw[slot];
+  unsigned *T = bv.word + (size_t)slot * bv.wslot;
+  unsigned *bitmap = bv.fim_bitmap + (size_t)slot * ((size_t)ntiles * fim::kT);
+  const int4 rect = bv.fim_rect[slot];
+  const int *reg = reinterpret_cast<const int *>(bv.fim_reg + (size_t)slot * fim::kRegNodes);
+  const float *vel = veln_all + (size_t)d.map * ((size_t)g.nnx * g.nnz);
+  fim::TileCtx C;
+  C.gx0 = C.gz0 = 0;
+  C.nnx = g.nnx;
+  C.nnz = g.nnz;
+  C.ri = g.earth;
+  C.dnx = g.dnx;
+  C.dnz = g.dnz;
+  C.bx0 = rect.x;
+  C.bz0 = rect.y;
+  C.bw = rect.z;
+  C.bh = rect.w;
+  C.box = reg;
+  // ---- prologue: region times into the field, dirty marks for the seeds and their not-yet-alive neighbours
+  for (int i = threadIdx.x; i < ntiles; i += blockDim.x) active[i] = 0;
+  for (int i = threadIdx.x; i < C.bw * C.bh; i += blockDim.x) {
+    const int st = reg[2 * i + 1];
+    if (st >= 0) {
+      const int bx = i / C.bh, bz = i - bx * C.bh;
+      T[L.at(C.bx0 + bx, C.bz0 + bz)] = (unsigned)reg[2 * i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C.bw * C.bh; i += blockDim.x) {
+    if (reg[2 * i + 1] <= 0) continue;
+    const int bx = i / C.bh, bz = i - bx * C.bh;
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      const int ex = bx + (q == 1 ? -1 : q == 2 ? 1 : 0), ez = bz + (q == 3 ? -1 : q == 4 ? 1 : 0);
+      const int gx = C.bx0 + ex, gz = C.bz0 + ez;
+      if (gx < 0 || gx >= C.nnx || gz < 0 || gz >= C.nnz) continue;
+      if (ex >= 0 && ex < C.bw && ez >= 0 && ez < C.bh && reg[2 * (ex * C.bh + ez) + 1] == 0) continue;
+      const int tx = gx / fim::kT, tz = gz / fim::kT;
+      atomicOr(bitmap + (size_t)(tx * L.ntz + tz) * fim::kT + (gx - tx * fim::kT), 1u << (gz - tz * fim::kT));
+      active[tx * L.ntz + tz] = 1;
+    }
+  }
+  __syncthreads();
+  // ---- rounds: every active tile once per round
+  int guard = 0;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      ctl->nlist = 0;
+      ctl->next = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x)
+      if (active[i]) {
+        active[i] = 0;
+        list[atomicAdd(&ctl->nlist, 1)] = (unsigned short)i;
+      }
+    __syncthreads();
+    const int nlist = ctl->nlist;
+    if (nlist == 0) break;
+    for (;;) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&ctl->next, 1);
+      k = __shfl_sync(kFull, k, 0);
+      if (k >= nlist) break;
+      fim_process_tile(tiles[wp], C, L, (int)list[k], T, bitmap, active, vel, risti_c, d.isx - 1, d.isz - 1, lane);
+    }
+    __syncthreads();
+    if (++guard > 64 * (L.ntx + L.ntz) + 1024) {  // no fixed point (cannot happen for a causal rule): report instead of hanging
+      if (threadIdx.x == 0) sw[slot].status = DSURF_ERR_HEAP;
+      break;
+    }
+  }
+}
+
+// Pipeline selection: dsurf_set_eikonal_mode() or DSURF_EIKONAL = exact | lps | fim (DSURF_EIKONAL_LPS=1 is the older
+// spelling of lps).  Default: the exact single-kernel march with 16 lanes per sweep (k_eikonal3).
+//   lps  k_refine + k_march_lps (exact, lane per sweep, warp-specialised).  Measured on B200 at cfg 3 (profiles/
+//        r02_eikonal_lps.md): 33 s per stage against 22.6 s -- with one lane per sweep every load touches 32 distinct lines
+//        and the slowest of 32 unrelated sweeps sets the pace of each acceptance; it needs 2.4x fewer DRAM bytes and 5x
+//        fewer issue slots per accepted node, but the machine is latency-, not throughput-bound on this path.
+//   fim  k_refine + k_fim_start + k_fim_march (eik_fim.cuh): not bit-exact by construction, deviations measured.
+static int g_eik_mode = -1;
+int eikonal_mode() {
+  if (g_eik_mode < 0) {
+    g_eik_mode = kEikExact16;
+    const char *e = getenv("DSURF_EIKONAL");
+    if (e && (!strcmp(e, "fim") || !strcmp(e, "FIM"))) g_eik_mode = kEikFim;
+    else if (e && !strcmp(e, "lps")) g_eik_mode = kEikLps;
+    else if (getenv("DSURF_EIKONAL_LPS")) g_eik_mode = kEikLps;
+  }
+  return g_eik_mode;
+}
+}  // namespace dsurf
+extern "C" int dsurf_set_eikonal_mode(int mode) {
+  if (mode < 0 || mode > 2) return DSURF_ERR_BAD_ARG;
+  dsurf::g_eik_mode = mode;
+  return DSURF_OK;
+}
+extern "C" int dsurf_get_eikonal_mode(void) { return dsurf::eikonal_mode(); }
+namespace dsurf {
+bool eikonal_uses_words(int mode) { return mode != kEikExact16; }
+
+void eikonal_word_layout(const Geom &g, int mode, int *wld, int *wpx, int *wpz, size_t *wslot) {
+  if (mode == kEikFim) {
+    const fim::Layout L = fim::make_layout(g.nnx, g.nnz);
+    *wld = L.pitch;
+    *wpx = fim::kHX;
+    *wpz = fim::kHZ;
+    *wslot = L.words();
+  } else {
+    *wld = g.nnz + 2 * lps::kPad;
+    *wpx = *wpz = lps::kPad;
+    *wslot = (size_t)(g.nnx + 2 * lps::kPad) * (g.nnz + 2 * lps::kPad);
+  }
+}
+size_t eikonal_fim_bitmap_words(const Geom &g) {
+  const fim::Layout L = fim::make_layout(g.nnx, g.nnz);
+  return (size_t)L.ntx * L.ntz * fim::kT;
+}
+
+// int2 entries of per-sweep heap slab the selected pipeline needs for capacity hcap
+int eikonal_slab_entries(int hcap, int mode) {
+  int n = hcap + 1;
+  if (mode == kEikLps) n = std::max(n, lps_slab_entries(hcap));
+  if (mode == kEikFim) n = std::max(n, fim::kRegNodes + 1);
+  return n;
+}
+
+// packed-record pipeline: sweeps that can be resident at once (its batches are sized to whole waves);
+// the word pipelines keep every sweep of a batch in memory and are limited by memory only
+int eikonal_resident_sweeps(int mode) {
+  if (mode != kEikExact16) return 0;
   const size_t sm = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
   int nb = 0;
   cudaFuncSetAttribute(k_eikonal3<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -1051,15 +1343,18 @@ int eikonal_resident_sweeps() {
 }
 
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
-                   const float *d_velv_all, const float *d_risti, BatchView bv, int *launches) {
+                   const float *d_velv_all, const float *d_risti, BatchView bv, int *launches, int mode) {
   if (nsw <= 0) return DSURF_OK;
   const long long ntot = (long long)nsw * g.nnx * g.nnz;
-  const long long nwtot = (long long)nsw * (g.nnx + 2 * lps::kPad) * (g.nnz + 2 * lps::kPad);
   SweepDesc *sw = const_cast<SweepDesc *>(d_sw);
   const int nt = kWarpsPerBlock * 32;
   const int per_block = kWarpsPerBlock * V3<16>::NG;
   const int grid3 = (nsw + per_block - 1) / per_block;
   const size_t smem = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
+  const fim::Layout L = fim::make_layout(g.nnx, g.nnz);
+  const int ntiles = L.ntx * L.ntz;
+  const size_t fsm = (size_t)kFimWarps * sizeof(fim::Tile) + sizeof(FimShared) + (size_t)((ntiles + 7) & ~7) * sizeof(unsigned short) +
+                     (size_t)((ntiles + 15) & ~15);
   static bool attr = false;
   if (!attr) {
     DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1067,9 +1362,10 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     DS_CUDA(cudaFuncSetAttribute(k_refine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DS_CUDA(cudaFuncSetAttribute(k_march_lps, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DS_CUDA(cudaFuncSetAttribute(k_march_lps, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+    DS_CUDA(cudaFuncSetAttribute(k_fim_march, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  if (legacy_v3()) {
+  if (mode == kEikExact16) {
     k_fill_nodes<<<sm_count() * 8, nt, 0, st>>>(bv.node, ntot);
     static const bool lazy = getenv("DSURF_EIKONAL_LAZY") != nullptr;
     if (lazy)
@@ -1080,8 +1376,26 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     if (launches) *launches += 2;
     return DSURF_OK;
   }
-  DS_CUDA(cudaMemsetAsync(bv.word, 0xFF, (size_t)nwtot * sizeof(unsigned), st));  // every node (and the frame) far
-  k_refine<16><<<grid3, nt, smem, st>>>(g, sw, nsw, d_velv_all, bv);
+  DS_CUDA(cudaMemsetAsync(bv.word, 0xFF, (size_t)nsw * bv.wslot * sizeof(unsigned), st));  // every node (and the frame) far
+  if (mode == kEikFim) {
+    if (ntiles > 65535 || fsm > 227 * 1024) {
+      set_error(__FILE__, __LINE__, "fast-iterative eikonal: grid too large for the per-sweep tile list");
+      return DSURF_ERR_BAD_ARG;
+    }
+    static size_t fsm_set = 0;
+    if (fsm > fsm_set) {
+      DS_CUDA(cudaFuncSetAttribute(k_fim_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      fsm_set = fsm;
+    }
+    DS_CUDA(cudaMemsetAsync(bv.fim_bitmap, 0, (size_t)nsw * ntiles * fim::kT * sizeof(unsigned), st));
+    k_refine<16><<<grid3, nt, smem, st>>>(g, sw, nsw, d_velv_all, bv, false);
+    k_fim_start<<<(nsw + 127) / 128, 128, 0, st>>>(g, sw, nsw, d_veln_all, d_risti, bv);
+    k_fim_march<<<nsw, kFimWarps * 32, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
+    DS_CUDA(cudaGetLastError());
+    if (launches) *launches += 3;
+    return DSURF_OK;
+  }
+  k_refine<16><<<grid3, nt, smem, st>>>(g, sw, nsw, d_velv_all, bv, true);
   DS_CUDA(cudaGetLastError());
   const size_t lsm = (size_t)kLpsHS * 32 * sizeof(int2) + 32 * sizeof(int2) + 4 * 32 * sizeof(float);
   k_march_lps<<<(nsw + 31) / 32, kLpsThreads, lsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv);

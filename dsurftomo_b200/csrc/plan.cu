@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "plan.cuh"
 #include "glue.cuh"
+#include "eik_fim.cuh"
 
 namespace dsurf {
 int launch_coef(cudaStream_t st, const float *d_vels, int nx, int ny, int nz, int brocher, float *coe_a,
@@ -82,7 +83,14 @@ struct dsurf_plan {
   std::vector<int> S_id_base = std::vector<int>(4, 0);
   // batch workspace
   int maxslots = 0, maxrays = 0, hcap = 0;
-  bool words = true;          // node state: one word per node (eik_lps.cuh) or legacy (time, status) records
+  bool words = true;          // node state: one word per node (eik_lps.cuh / eik_fim.cuh) or packed (time, status) records
+  int mode = 0;               // eikonal pipeline this plan was sized for (kEikExact16 / kEikLps / kEikFim)
+  int wld = 0, wpx = 0, wpz = 0;
+  size_t wslot = 0;           // word layout (BatchView)
+  DevBuf<unsigned> fim_bitmap, fim_rw;
+  DevBuf<int2> fim_reg;
+  DevBuf<int4> fim_rect;
+  DevBuf<unsigned char> fim_flag;
   DevBuf<int2> node, noder, box, seed;
   DevBuf<unsigned> word;
   DevBuf<int> nseed;
@@ -337,7 +345,8 @@ static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const floa
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
   p->hcap = 8 * (p->g.nnx + p->g.nnz) + 1024;
-  if (eikonal_uses_words()) {
+  p->mode = eikonal_mode();
+  if (p->mode == kEikLps) {
     // the blocked heap slab (eikonal.cu: lps_gaddr) is allocated in whole level groups: capacities 2^(10+3k) - 1.
     // Measured narrow bands at 1025^2: mean 1.8-2.8 k, max 4.1 k entries (tests/host/lps_host_check.cpp).
     int cap = 1023;
@@ -352,11 +361,14 @@ static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const floa
   const size_t fdm_per_ray = forward_only ? sizeof(float) : (size_t)(p->g.nvz + 2) * (p->g.nvx + 2) * sizeof(float);
   int maxnrc = 1;
   for (auto &gi : p->gathers) maxnrc = std::max(maxnrc, gi.nrc);
-  p->words = eikonal_uses_words();
-  const size_t slab = (size_t)eikonal_slab_entries(p->hcap);
+  p->words = eikonal_uses_words(p->mode);
+  const size_t slab = (size_t)eikonal_slab_entries(p->hcap, p->mode);
   const size_t kBox = (size_t)(2 * kSgs + 1) * (2 * kSgs + 1);
-  const size_t Nw = (size_t)(p->g.nnx + 6) * (p->g.nnz + 6);  // padded word array of the round-2 march (eik_lps.cuh, kPad = 3)
-  const size_t per_slot = (p->words ? Nw * sizeof(unsigned) : Nc * sizeof(int2)) +
+  eikonal_word_layout(p->g, p->mode, &p->wld, &p->wpx, &p->wpz, &p->wslot);
+  const size_t Nw = p->wslot;  // padded word array of the word pipelines
+  const size_t fim_bm = p->mode == kEikFim ? eikonal_fim_bitmap_words(p->g) : 0;
+  const size_t fim_slot = p->mode == kEikFim ? fim_bm * sizeof(unsigned) + (size_t)fim::kRegNodes * (sizeof(int2) + sizeof(unsigned) + 1) + sizeof(int4) : 0;
+  const size_t per_slot = fim_slot + (p->words ? Nw * sizeof(unsigned) : Nc * sizeof(int2)) +
                           (size_t)kRefMax * kRefMax * (sizeof(int2) + sizeof(float)) + slab * sizeof(int2) +
                           kRefMax * sizeof(float) + sizeof(SweepDesc) + kBox * 2 * sizeof(int2) + sizeof(int);
   // rays are traced and assembled in chunks of at most maxrays (their dense fdm slabs dominate otherwise)
@@ -379,7 +391,7 @@ static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const floa
   long long ms = (long long)(budget / per_slot);
   ms = std::min<long long>(ms, std::max<long long>(nsw_total, 1));
   {  // legacy pipeline: batches of at most one resident wave (larger launches would run as equal-length waves)
-    const long long res = eikonal_resident_sweeps();
+    const long long res = eikonal_resident_sweeps(p->mode);
     if (res > 0) ms = std::min<long long>(ms, res);
   }
   if (const char *e = getenv("DSURF_MAXSLOTS")) ms = std::min<long long>(ms, std::max(1, atoi(e)));  // test hook: force batching
@@ -391,6 +403,13 @@ static int plan_create_impl(dsurf_plan **out, int nx, int ny, int nz, const floa
     bad |= p->box.reserve((size_t)p->maxslots * kBox) != cudaSuccess;
     bad |= p->seed.reserve((size_t)p->maxslots * kBox) != cudaSuccess;
     bad |= p->nseed.reserve((size_t)p->maxslots) != cudaSuccess;
+    if (p->mode == kEikFim) {
+      bad |= p->fim_bitmap.reserve((size_t)p->maxslots * fim_bm) != cudaSuccess;
+      bad |= p->fim_rw.reserve((size_t)p->maxslots * fim::kRegNodes) != cudaSuccess;
+      bad |= p->fim_reg.reserve((size_t)p->maxslots * fim::kRegNodes) != cudaSuccess;
+      bad |= p->fim_flag.reserve((size_t)p->maxslots * fim::kRegNodes) != cudaSuccess;
+      bad |= p->fim_rect.reserve((size_t)p->maxslots) != cudaSuccess;
+    }
   } else {
     bad |= p->node.reserve((size_t)p->maxslots * Nc) != cudaSuccess;
   }
@@ -666,7 +685,16 @@ static BatchView batch_view(dsurf_plan *p) {
   bv.box = p->box.p;
   bv.seed = p->seed.p;
   bv.nseed = p->nseed.p;
-  bv.slab = eikonal_slab_entries(p->hcap);
+  bv.slab = eikonal_slab_entries(p->hcap, p->mode);
+  bv.wld = p->wld;
+  bv.wpx = p->wpx;
+  bv.wpz = p->wpz;
+  bv.wslot = p->wslot;
+  bv.fim_bitmap = p->fim_bitmap.p;
+  bv.fim_rw = p->fim_rw.p;
+  bv.fim_reg = p->fim_reg.p;
+  bv.fim_rect = p->fim_rect.p;
+  bv.fim_flag = p->fim_flag.p;
   bv.noder = p->noder.p;
   bv.velr = p->velr.p;
   bv.hent = p->hent.p;
@@ -689,7 +717,7 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
   for (int attempt = 0; attempt < 3; attempt++) {
     const BatchView bv = batch_view(p);
     cudaEventRecord(p->ev[0], st);
-    DS_CHECK(launch_eikonal(st, p->g, p->d_sw.p, nsw, p->veln_all.p, p->velv_all.p, p->risti_c.p, bv, launches));
+    DS_CHECK(launch_eikonal(st, p->g, p->d_sw.p, nsw, p->veln_all.p, p->velv_all.p, p->risti_c.p, bv, launches, p->mode));
     cudaEventRecord(p->ev[1], st);
     DS_CUDA(cudaMemcpyAsync(hsw.data(), p->d_sw.p, nsw * sizeof(SweepDesc), cudaMemcpyDeviceToHost, st));
     DS_CUDA(cudaStreamSynchronize(st));
@@ -708,7 +736,7 @@ static int run_batch(dsurf_plan *p, std::vector<SweepDesc> &hsw, std::vector<Ray
       return DSURF_ERR_HEAP;
     }
     p->hcap = (int)std::min<long long>(maxbt, (long long)p->hcap * 8 + 7);
-    if (p->hent.reserve((size_t)p->maxslots * (size_t)eikonal_slab_entries(p->hcap))) {
+    if (p->hent.reserve((size_t)p->maxslots * (size_t)eikonal_slab_entries(p->hcap, p->mode))) {
       set_error(__FILE__, __LINE__, "cudaMalloc failed (heap growth)");
       return DSURF_ERR_CUDA;
     }
@@ -895,8 +923,8 @@ extern "C" int dsurf_plan_debug_sweep(dsurf_plan *p, int gidx, int ig, float *ve
   const SweepDesc &d = hsw[0];
   if (veln) DS_CUDA(cudaMemcpy(veln, p->veln_all.p + (size_t)d.map * Nc, Nc * sizeof(float), cudaMemcpyDeviceToHost));
   if (ttn && p->words) {  // every node alive: word = time; strip the 3-node frame
-    const size_t wld = (size_t)g.nnz + 6;
-    DS_CUDA(cudaMemcpy2D(ttn, g.nnz * sizeof(float), p->word.p + 3 * wld + 3, wld * sizeof(float), g.nnz * sizeof(float),
+    const size_t wld = (size_t)p->wld;
+    DS_CUDA(cudaMemcpy2D(ttn, g.nnz * sizeof(float), p->word.p + p->wpx * wld + p->wpz, wld * sizeof(float), g.nnz * sizeof(float),
                          g.nnx, cudaMemcpyDeviceToHost));
   } else if (ttn) {
     std::vector<int2> tmp(Nc);

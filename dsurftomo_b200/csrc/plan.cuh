@@ -71,7 +71,11 @@ struct RayDesc {              // one receiver of one sweep
 // per-sweep state of a batch slot (device pointers)
 struct BatchView {
   int2 *node;        // legacy pipeline: [slot][nnx*nnz] packed (float bits of ttn, nsts), iz fastest
-  unsigned *word;    // [slot][nnx*nnz] one word per coarse node (eik_lps.cuh); alive = fp32 time; null in legacy mode
+  unsigned *word;    // [slot][wslot] one word per coarse node (alive = fp32 time), node (ix, iz) 0-based at
+                     // (ix + wpx) * wld + iz + wpz; null in the packed-record mode.  Lane-per-sweep march: 3-node frame
+                     // (eik_lps.cuh); fast-iterative march: tile-aligned rows (eik_fim.cuh, Layout)
+  int wld, wpx, wpz;
+  size_t wslot;
   int2 *box;         // [slot][289] injection scratch (status, time) of the refined box
   int2 *seed;        // [slot][289] (key bits, node) of the coarse close nodes in travel(urg=2)'s insertion order
   int *nseed;        // [slot]
@@ -81,14 +85,27 @@ struct BatchView {
   int2 *hent;        // [slot][slab] (key,node) heap entries beyond the shared-memory part
   const float *ristr; // [slot][129] earth*sin(gorx+(ix-1)*drnx), host libm
   int hcap;
+  // fast-iterative march (eik_fim.cuh)
+  unsigned *fim_bitmap;     // [slot][tiles * 32] node-level dirty bits, one word per tile row
+  int2 *fim_reg;            // [slot][kRegNodes] start-up region after hand-over: (time bits, status 0 alive / 1 seed / -1 far)
+  int4 *fim_rect;           // [slot] region rectangle (rx0, rz0, rw, rh)
+  unsigned *fim_rw;         // [slot][kRegNodes] start-up scratch: region words
+  unsigned char *fim_flag;  // [slot][kRegNodes] start-up scratch: seed / raised-key flags
 };
+
+// eikonal pipelines (dsurf_set_eikonal_mode / DSURF_EIKONAL): 0 exact, 16 lanes per sweep, packed records (default);
+// 1 exact, lane per sweep, one word per node; 2 block-level fast-iterative sweep after an exact start-up
+enum { kEikExact16 = 0, kEikLps = 1, kEikFim = 2 };
+int eikonal_mode();   // mode newly created plans take
 
 int launch_dice(cudaStream_t st, const Geom &g, const double *d_pv_map, float *d_velv, float *d_veln);
 int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int nsw, const float *d_veln_all,
-                   const float *d_velv_all, const float *d_risti, BatchView bv, int *launches);
-int eikonal_resident_sweeps();        // legacy pipeline only; 0 = limited by memory only
-int eikonal_slab_entries(int hcap);
-bool eikonal_uses_words();
+                   const float *d_velv_all, const float *d_risti, BatchView bv, int *launches, int mode);
+int eikonal_resident_sweeps(int mode);        // packed-record pipeline only; 0 = limited by memory only
+int eikonal_slab_entries(int hcap, int mode);
+bool eikonal_uses_words(int mode);
+void eikonal_word_layout(const Geom &g, int mode, int *wld, int *wpx, int *wpz, size_t *wslot);
+size_t eikonal_fim_bitmap_words(const Geom &g);
 int launch_rays(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, const RayDesc *d_rays, int nrays,
                 const float *d_veln_all, BatchView bv, float *d_tt, float *d_fdm, int4 *d_bbox,
                 int *d_rbint, int *d_err, float2 *d_path = nullptr, int *d_path_n = nullptr, int path_cap = 0);

@@ -70,14 +70,14 @@ __device__ __forceinline__ float sin_cr(float y) {
 __device__ __forceinline__ float node_t(const int2 *n, size_t i) { return __int_as_float(n[i].x); }
 // coarse travel times: one word per node (eik_lps.cuh; every node is alive after the sweep, word = time)
 // or the legacy packed (time, status) records
-struct CoarseT {  // i = (ix - 1) * nnz + (iz - 1); the word array carries a 3-node frame (eik_lps.cuh, kPad)
+struct CoarseT {  // i = (ix - 1) * nnz + (iz - 1); the word array is padded (BatchView::wld, wpx, wpz)
   const int2 *n;
   const unsigned *w;
-  int nnz;
+  int nnz, wld, wpx, wpz;
   __device__ __forceinline__ float t(size_t i) const {
     if (!w) return __int_as_float(n[i].x);
     const size_t x = i / (size_t)nnz, z = i - x * (size_t)nnz;
-    return __uint_as_float(w[(x + 3) * (size_t)(nnz + 6) + z + 3]);
+    return __uint_as_float(w[(x + wpx) * (size_t)wld + z + wpz]);
   }
 };
 
@@ -119,8 +119,11 @@ k_rays(Geom g, const SweepDesc *__restrict__ sw, const RayDesc *__restrict__ ray
   const float *veln = veln_all + (size_t)d.map * Nc;
   CoarseT node;
   node.n = bv.word ? nullptr : bv.node + (size_t)rd.sweep * Nc;
-  node.w = bv.word ? bv.word + (size_t)rd.sweep * ((size_t)(g.nnx + 6) * (g.nnz + 6)) : nullptr;
+  node.w = bv.word ? bv.word + (size_t)rd.sweep * bv.wslot : nullptr;
   node.nnz = g.nnz;
+  node.wld = bv.wld;
+  node.wpx = bv.wpx;
+  node.wpz = bv.wpz;
   const int2 *noder = bv.noder + (size_t)rd.sweep * kRefMax * kRefMax;
   const int nnx = g.nnx, nnz = g.nnz, nnxr = d.nrnx, nnzr = d.nrnz;
   const float gox = g.gox, goz = g.goz, dnx = g.dnx, dnz = g.dnz, dvx = g.dvx, dvz = g.dvz;

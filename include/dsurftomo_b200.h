@@ -49,6 +49,18 @@ const char *dsurf_last_error(void);
 int dsurf_set_device(int device);
 /* library build info: "sm_100a fmad=off ..." */
 const char *dsurf_build_info(void);
+/* Eikonal pipeline used by plans (and drop-in calls) created AFTER the call; initial value from the environment
+ * variable DSURF_EIKONAL = exact | lps | fim.
+ *   0 exact  the reference's fast marching replayed in its exact heap pop order (travel/fouds2/addtree/downtree/updtree,
+ *            CalSurfG.f90:288-921): travel times bit-identical to the reference.  Default.
+ *   1 lps    the same exact march, one lane per sweep (slower on B200, kept for A/B runs).
+ *   2 fim    block-level fast-iterative sweep of north_star (no heap; 32 x 32 tiles relaxed in shared memory) after an
+ *            exact start-up around the source.  Iterates the reference's own causal update rule with the reference's
+ *            fp32 arithmetic, so most nodes come out bit-identical; where the reference's heap leaves time order (equal
+ *            keys, raised keys) times differ in the last bits (measured: <= 4e-6 relative on smooth models,
+ *            profiles/r02_fim_parity.md).  Several times faster. */
+int dsurf_set_eikonal_mode(int mode);
+int dsurf_get_eikonal_mode(void);
 
 /* ------------------------------------------------------------------ (1) Fortran drop-ins */
 
