@@ -58,6 +58,9 @@ LPS_HD Layout make_layout(int nnx, int nnz) {
   return L;
 }
 
+#if !defined(__CUDA_ARCH__) && defined(DSURF_FIM_CROSSCHECK)
+static long g_cross_total = 0, g_cross_mismatch = 0, g_generic_calls = 0;
+#endif
 LPS_HD float as_f(uint32_t w) { return lps::bits2f((int)w); }
 LPS_HD uint32_t as_u(float f) { return (uint32_t)lps::f2bits(f); }
 
@@ -67,10 +70,18 @@ LPS_HD uint32_t alive_word(uint32_t w, float t) {
   return al ? (w & 0x7FFFFFFFu) : lps::kFar;
 }
 
-// The causal rule for the node whose tile-copy word is *c (see the header).  seed: injected time of a close node, else
-// +inf.  in[0..3]: the neighbour ix-1 / ix+1 / iz-1 / iz+1 lies inside the grid (the reference skips the side
-// otherwise, :604-605).  Returns the node's time (+inf: nothing reaches it yet).
-LPS_HD float rule(const uint32_t *c, float seed, float slown, float ri, float risti, float dnx, float dnz, const bool in[4]) {
+// The causal rule for the node whose tile-copy word is *c (see the header), evaluated the plain way: one complete
+// fouds2 per neighbour that is popped before the node.  seed: injected time of a close node, else +inf.  in[0..3]: the
+// neighbour ix-1 / ix+1 / iz-1 / iz+1 lies inside the grid (the reference skips the side otherwise, :604-605).
+// Returns the node's time (+inf: nothing reaches it yet).  rule() below is the same function, faster.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+float rule_generic(const uint32_t *c, float seed, float slown, float ri, float risti, float dnx, float dnz, bool in0, bool in1,
+                   bool in2, bool in3) {
+  const bool in[4] = {in0, in1, in2, in3};
   const uint32_t w1[4] = {c[-kPitch], c[kPitch], c[-1], c[1]};
   const uint32_t w2[4] = {c[-2 * kPitch], c[2 * kPitch], c[-2], c[2]};
   // neighbours popped during the pass: inside the grid, not alive before it, reached (finite)
@@ -78,7 +89,6 @@ LPS_HD float rule(const uint32_t *c, float seed, float slown, float ri, float ri
   float t1 = (in[1] && w1[1] < kInf) ? as_f(w1[1]) : as_f(kInf);
   float t2 = (in[2] && w1[2] < kInf) ? as_f(w1[2]) : as_f(kInf);
   float t3 = (in[3] && w1[3] < kInf) ? as_f(w1[3]) : as_f(kInf);
-  // sorting network (ascending)
 #define DSURF_FIM_CX(a, b) \
   {                        \
     const float lo = a < b ? a : b, hi = a < b ? b : a; \
@@ -111,7 +121,65 @@ LPS_HD float rule(const uint32_t *c, float seed, float slown, float ri, float ri
   return v;
 }
 
-// ---- per-warp working set of a tile (shared memory on the device)
+// The same rule for the COMMON case, in straight-line code.  fouds2's result for an alive set A is the minimum over
+// the (up to four) quadrants (x side, z side) of: the two-leg solution if both sides are alive, the one-leg solution of
+// the alive side if only one is.  A leg is (T1, T2, second-order flag) of one side; second order needs the 2-away node
+// alive and T1 > T2 (:620-663), and a 2-away node EARLIER than its 1-away node is alive whenever that one is, so a leg --
+// and with it every quadrant solution -- does not depend on the moment of the evaluation.  Almost every node ends up
+// with at most ONE alive side per axis (the upwind one: X1 = the earlier of ix-1 / ix+1, Z1 likewise); then the whole
+// history is
+//     v1 = one-leg(first of X1, Z1);   if the other one is popped before v1:   v = min(two-leg(X1, Z1), one-leg(X1) if
+//     the far z side exists, one-leg(Z1) if the far x side exists)
+// i.e. three quadrant solutions, each computed once (the plain form evaluates 5-7 quadrants).  Everything else -- a
+// second side of an axis popped in time (colliding fronts), equal times on one axis, seeds and nodes alive before the
+// pass (start-up region) -- is detected and handed to rule_generic.  Both forms call lps::quad on the same operands,
+// so they agree bit for bit; the host replay (tests/host/fim_host_check.cpp) compares them on every evaluation.
+LPS_HD float rule(const uint32_t *c, float seed, float slown, float ri, float risti, float dnx, float dnz, const bool in[4]) {
+  const uint32_t wxm = c[-kPitch], wxp = c[kPitch], wzm = c[-1], wzp = c[1];
+  const float inf = as_f(kInf);
+  // popped neighbours: inside the grid, not alive before the pass (sign flag), reached (finite)
+  const float txm = (in[0] && wxm < kInf) ? as_f(wxm) : inf, txp = (in[1] && wxp < kInf) ? as_f(wxp) : inf;
+  const float tzm = (in[2] && wzm < kInf) ? as_f(wzm) : inf, tzp = (in[3] && wzp < kInf) ? as_f(wzp) : inf;
+  const bool anyinit = (in[0] && (int)wxm < 0) || (in[1] && (int)wxp < 0) || (in[2] && (int)wzm < 0) || (in[3] && (int)wzp < 0);
+  const bool xp = txp < txm, zp = tzp < tzm;                 // upwind side of each axis
+  const float tx = xp ? txp : txm, tx2 = xp ? txm : txp;     // its time, the far side's time
+  const float tz = zp ? tzp : tzm, tz2 = zp ? tzm : tzp;
+  bool generic = anyinit || seed < inf || (tx2 == tx && tx < inf) || (tz2 == tz && tz < inf);
+  float v = inf;
+  if (!generic && (tx < inf || tz < inf)) {
+    // legs of the two upwind sides
+    const uint32_t wx2 = xp ? c[2 * kPitch] : c[-2 * kPitch], wz2 = zp ? c[2] : c[-2];
+    const float Tx2 = as_f(wx2 & 0x7FFFFFFFu), Tz2 = as_f(wz2 & 0x7FFFFFFFu);
+    const bool sox = tx > Tx2, soz = tz > Tz2;  // 2-away node reached (or alive before the pass) and earlier
+    const bool xfar_in = xp ? in[0] : in[1], zfar_in = zp ? in[2] : in[3];  // the far side of each axis lies inside the grid
+    float q1x = inf, q1z = inf, q2 = inf;
+    if (tx < inf) lps::quad(tx, Tx2, true, sox, 0.0f, 0.0f, false, false, slown, ri, risti, dnx, dnz, q1x);
+    if (tz < inf) lps::quad(0.0f, 0.0f, false, false, tz, Tz2, true, soz, slown, ri, risti, dnx, dnz, q1z);
+    const bool xfirst = tx < tz, tie = tx == tz;
+    const float v1 = xfirst ? q1x : q1z;          // after the first pop (not evaluated on a tie)
+    const float tb = xfirst ? tz : tx;            // the other axis' upwind side ...
+    const float toa = xfirst ? tx2 : tz2;         // ... and the first axis' far side: whichever is earlier comes next
+    if (!tie && toa <= tb && toa < v1) generic = true;  // the far side of the first axis is popped in time (or ties with tb)
+    const bool both = tie || (tb < toa && tb < v1);
+    if (!tie && !generic && !both) v = v1;
+    if (both && !generic) {
+      lps::quad(tx, Tx2, true, sox, tz, Tz2, true, soz, slown, ri, risti, dnx, dnz, q2);
+      float v2 = q2;
+      if (zfar_in) v2 = q1x < v2 ? q1x : v2;
+      if (xfar_in) v2 = q1z < v2 ? q1z : v2;
+      const float t3 = tx2 < tz2 ? tx2 : tz2;
+      if (t3 < v2) generic = true;  // a third side is popped in time
+      v = v2;
+    }
+  }
+#if !defined(__CUDA_ARCH__) && defined(DSURF_FIM_CROSSCHECK)
+  if (generic) g_generic_calls++;
+#endif
+  if (generic) return rule_generic(c, seed, slown, ri, risti, dnx, dnz, in[0], in[1], in[2], in[3]);
+  return v;
+}
+
+// ---- per-warp working set of a tile: host replay (with a slowness copy); the device keeps TileD in shared memory
 struct Tile {
   uint32_t t[kTileWords];  // times: rows -kHX..kT+kHX-1, columns -kHZ..kT+kHZ-1
   float slow[kT * kT];     // 1 / velocity, [x][z]
@@ -119,6 +187,15 @@ struct Tile {
   uint32_t dirty[kT];      // word x: bit z = node (x, z) must be re-evaluated
   uint32_t hx[4];          // marks for the halo rows x = -2, -1, kT, kT+1 (bit z): nodes of the x-neighbour tiles
   uint32_t hz[4];          // marks for the halo columns z = -2, -1, kT, kT+1 (bit x)
+  LPS_HD uint32_t *at(int x, int z) { return t + (x + kHX) * kPitch + (z + kHZ); }
+};
+
+struct TileD {             // 6048 bytes: 24-32 warps (= sweeps) per SM
+  uint32_t t[kTileWords];
+  float risti[kT];
+  uint32_t dirty[kT];
+  uint32_t hx[4];
+  uint32_t hz[4];
   LPS_HD uint32_t *at(int x, int z) { return t + (x + kHX) * kPitch + (z + kHZ); }
 };
 
@@ -151,39 +228,59 @@ LPS_HD float seed_of(const TileCtx &C, int gx, int gz) {
 // Re-evaluates tile node (x, z) (its dirty bit is set): clears the bit, applies the rule, and if the time changed stores
 // it and marks the stencil users that can see the change.  Lanes of one anti-diagonal call this concurrently: their
 // nodes are never in each other's stencils.  Returns true if the time changed.
-LPS_HD bool relax_node(Tile &tl, const TileCtx &C, int x, int z) {
+template <class TL>
+LPS_HD bool relax_node(TL &tl, const TileCtx &C, int x, int z, float slown) {
   DSURF_FIM_AND(&tl.dirty[x], ~(1u << z));
   uint32_t *c = tl.at(x, z);
   const uint32_t old = *c;
   if ((int)old < 0) return false;  // alive before the pass: never recomputed
   const int gx = C.gx0 + x, gz = C.gz0 + z;
   const bool in[4] = {gx - 1 >= 0, gx + 1 < C.nnx, gz - 1 >= 0, gz + 1 < C.nnz};
-  const float v = rule(c, seed_of(C, gx, gz), tl.slow[x * kT + z], C.ri, tl.risti[x], C.dnx, C.dnz, in);
+  const float v = rule(c, seed_of(C, gx, gz), slown, C.ri, tl.risti[x], C.dnx, C.dnz, in);
+#if !defined(__CUDA_ARCH__) && defined(DSURF_FIM_CROSSCHECK)
+  {  // host replay: the cached-quadrant rule against the plain one, on every evaluation
+    const float vg = rule_generic(c, seed_of(C, gx, gz), slown, C.ri, tl.risti[x], C.dnx, C.dnz, in[0], in[1], in[2], in[3]);
+    g_cross_total++;
+    if (as_u(vg) != as_u(v)) g_cross_mismatch++;
+  }
+#endif
   const uint32_t nw = as_u(v);
   if (nw == old) return false;
   *c = nw;
   const float mn = v < as_f(old) ? v : as_f(old);
+  // users: the 8 nodes whose stencil holds this node.  A user earlier than both values never looks at it (the rule only
+  // takes nodes popped before the user); users alive before the pass are never recomputed.
+  unsigned zmask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int q = 0; q < 8; q++) {
-    const int d = (q & 1) ? 2 : 1, sg = (q & 2) ? 1 : -1;
-    const int ux = x + ((q < 4) ? sg * d : 0), uz = z + ((q < 4) ? 0 : sg * d);
-    const int ugx = C.gx0 + ux, ugz = C.gz0 + uz;
-    if (ugx < 0 || ugx >= C.nnx || ugz < 0 || ugz >= C.nnz) continue;
-    const uint32_t uw = *tl.at(ux, uz);
-    if ((int)uw < 0) continue;
-    if (mn >= as_f(uw)) continue;  // the user is earlier than both values: the rule never looks at this node
-    if (ux < 0)
-      DSURF_FIM_OR(&tl.hx[ux + 2], 1u << uz);
-    else if (ux >= kT)
-      DSURF_FIM_OR(&tl.hx[ux - kT + 2], 1u << uz);
-    else if (uz < 0)
-      DSURF_FIM_OR(&tl.hz[uz + 2], 1u << ux);
+  for (int q = 0; q < 4; q++) {
+    const int dz = q == 0 ? -2 : q == 1 ? -1 : q == 2 ? 1 : 2;
+    const int uz = z + dz, ugz = gz + dz;
+    const uint32_t uw = c[dz];
+    if (ugz < 0 || ugz >= C.nnz || (int)uw < 0 || mn >= as_f(uw)) continue;
+    if (uz < 0)
+      DSURF_FIM_OR(&tl.hz[uz + 2], 1u << x);
     else if (uz >= kT)
-      DSURF_FIM_OR(&tl.hz[uz - kT + 2], 1u << ux);
+      DSURF_FIM_OR(&tl.hz[uz - kT + 2], 1u << x);
     else
-      DSURF_FIM_OR(&tl.dirty[ux], 1u << uz);
+      zmask |= 1u << uz;
+  }
+  if (zmask) DSURF_FIM_OR(&tl.dirty[x], zmask);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; q++) {
+    const int dx = q == 0 ? -2 : q == 1 ? -1 : q == 2 ? 1 : 2;
+    const int ux = x + dx, ugx = gx + dx;
+    const uint32_t uw = c[dx * kPitch];
+    if (ugx < 0 || ugx >= C.nnx || (int)uw < 0 || mn >= as_f(uw)) continue;
+    if (ux < 0)
+      DSURF_FIM_OR(&tl.hx[ux + 2], 1u << z);
+    else if (ux >= kT)
+      DSURF_FIM_OR(&tl.hx[ux - kT + 2], 1u << z);
+    else
+      DSURF_FIM_OR(&tl.dirty[ux], 1u << z);
   }
   return true;
 }

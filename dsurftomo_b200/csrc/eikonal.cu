@@ -1027,10 +1027,9 @@ k_march_lps(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict
 
 // =============================================================================================
 // Fast-iterative pipeline (DSURF_EIKONAL=fim): k_refine (exact, as above) -> k_fim_start (exact start-up of the
-// coarse pass, one thread per sweep) -> k_fim_march (block-level fast-iterative sweep, one CTA per sweep, one warp per
-// 32 x 32 tile).  Algorithm, its relation to the reference's heap march and the measured deviations: eik_fim.cuh.
+// coarse pass, one thread per sweep) -> k_fim_march (block-level fast-iterative sweep: one warp per sweep relaxes its
+// 32 x 32 tiles in shared memory).  Algorithm, its relation to the reference's heap march and the measured deviations: eik_fim.cuh.
 // =============================================================================================
-constexpr int kFimWarps = 8;
 
 __global__ void __launch_bounds__(128)
 k_fim_start(Geom g, const SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all,
@@ -1077,18 +1076,49 @@ k_fim_start(Geom g, const SweepDesc *__restrict__ sw, int nsw, const float *__re
   }
 }
 
-struct FimShared {       // per-CTA control block (one CTA = one sweep)
-  int nlist, next, pad0, pad1;
-};
+// ---- bulk asynchronous copies (TMA engine, 1-D form) with an mbarrier: tile rows global -> shared
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
-// one warp relaxes one tile: load (times + halo, slowness), anti-diagonal walks, store, marks for the neighbours
-__device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fim::Layout L, int tile, unsigned *T,
-                                 unsigned *bitmap, unsigned char *active, const float *vel, const float *risti_c, int srcx,
-                                 int srcz, int lane) {
+// One WARP owns one sweep from start to finish: no block-level synchronisation anywhere, the relaxation order is a
+// pure function of the sweep (results do not depend on scheduling), and 24 sweeps are resident per SM.
+constexpr int kFimSweepsPerCta = 4;
+constexpr int kFimMaxWordsPerLane = 5;  // tile-activity bitmask: up to 5 * 32 * 32 = 5120 tiles (71 x 71: 2272^2 nodes)
+
+// the warp relaxes one tile: load (times + halo), anti-diagonal walks, store, marks for the neighbour tiles
+template <bool TMA>
+__device__ __forceinline__ void fim_process_tile(fim::TileD &tl, const fim::TileCtx &Cb, const fim::Layout L, int tile, unsigned *T,
+                                                 unsigned *bitmap, unsigned *active, const float *vel, const float *risti_c,
+                                                 int srcx, int srcz, int lane, unsigned long long *bar, unsigned &phase) {
   const int tx = tile / L.ntz, tz = tile - tx * L.ntz;
   unsigned *bm = bitmap + (size_t)tile * fim::kT;
-  const unsigned mydirty = atomicExch(bm + lane, 0u);
-  if (!__any_sync(kFull, mydirty != 0)) return;  // activated by a neighbour whose marks were consumed already
+  const unsigned mydirty = bm[lane];
+  if (!__any_sync(kFull, mydirty != 0)) return;
+  bm[lane] = 0;
   fim::TileCtx C = Cb;
   C.gx0 = tx * fim::kT;
   C.gz0 = tz * fim::kT;
@@ -1098,9 +1128,19 @@ __device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fi
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(T + (size_t)C.gx0 * L.pitch + C.gz0);  // row gx0 - kHX, column gz0 - kHZ
     constexpr int kVecRow = fim::kPitch / 4;
+    if (TMA) {
+      // the 36 rows (160 bytes each, 16-byte aligned) go through the TMA engine; one mbarrier per warp counts the bytes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the tile buffer
+      if (lane == 0) mbar_expect_tx(bar, fim::kRows * fim::kPitch * 4);
+      __syncwarp();
+      for (int r = lane; r < fim::kRows; r += 32)
+        bulk_g2s(tl.t + r * fim::kPitch, src + (size_t)r * (L.pitch / 4), fim::kPitch * 4, bar);
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
     for (int i = lane; i < fim::kRows * kVecRow; i += 32) {
       const int r = i / kVecRow, c4 = i - r * kVecRow;
-      uint4 v = __ldcg(src + (size_t)r * (L.pitch / 4) + c4);
+      uint4 v = TMA ? *reinterpret_cast<const uint4 *>(tl.t + r * fim::kPitch + 4 * c4) : src[(size_t)r * (L.pitch / 4) + c4];
       v.x = (int)v.x < 0 ? fim::kInf : v.x;
       v.y = (int)v.y < 0 ? fim::kInf : v.y;
       v.z = (int)v.z < 0 ? fim::kInf : v.z;
@@ -1118,13 +1158,6 @@ __device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fi
     }
   }
   {
-    const int gz = C.gz0 + lane;
-    for (int x = 0; x < fim::kT; x++) {
-      const int gx = C.gx0 + x;
-      float sl = 1.0f;
-      if (gx < C.nnx && gz < C.nnz) sl = 1.0f / __ldg(vel + (size_t)gx * C.nnz + gz);
-      tl.slow[x * fim::kT + lane] = sl;
-    }
     const int gx = C.gx0 + lane;
     tl.risti[lane] = gx < C.nnx ? __ldg(risti_c + gx) : 0.0f;
     tl.dirty[lane] = mydirty;
@@ -1136,14 +1169,24 @@ __device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fi
   const int sx0 = (C.gx0 + fim::kT / 2 >= srcx) ? 1 : -1, sz0 = (C.gz0 + fim::kT / 2 >= srcz) ? 1 : -1;
   bool changed = false;
   volatile unsigned *vdirty = tl.dirty;
+  const float *velrow = vel + (size_t)min(C.gx0 + lane, C.nnx - 1) * C.nnz;
   for (int w = 0; w < 32; w++) {
     if (!__any_sync(kFull, vdirty[lane] != 0)) break;
     const int sx = (w & 1) ? -sx0 : sx0, sz = (w & 2) ? -sz0 : sz0;
+    float slow_pf = 0.0f;  // slowness of this lane's node on the NEXT diagonal, loaded one step ahead (off the critical path)
+    int z_pf = -2;
     for (int dg = 0; dg < 2 * fim::kT - 1; dg++) {
       const int z = fim::diag_z(lane, dg, sx, sz);
       const bool mine = z >= 0 && ((vdirty[lane] >> z) & 1u);
       if (!__any_sync(kFull, mine)) continue;
-      if (mine) changed |= fim::relax_node(tl, C, lane, z);
+      float sl = slow_pf;
+      if (mine && z_pf != z) sl = 1.0f / __ldg(velrow + min(C.gz0 + z, C.nnz - 1));
+      const int zn = fim::diag_z(lane, dg + 1, sx, sz);
+      if (zn >= 0) {
+        slow_pf = 1.0f / __ldg(velrow + min(C.gz0 + zn, C.nnz - 1));
+        z_pf = zn;
+      }
+      if (mine) changed |= fim::relax_node(tl, C, lane, z, sl);
       __syncwarp();
     }
   }
@@ -1157,8 +1200,6 @@ __device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fi
       if (gx < C.nnx && gz < C.nnz && (int)w >= 0) T[L.at(gx, gz)] = (w == fim::kInf) ? fim::kFarG : w;
     }
   }
-  __threadfence_block();
-  __syncwarp();
   {
     // x-neighbours: halo rows -2, -1 are rows 30, 31 of tile (tx - 1, tz); rows 32, 33 are rows 0, 1 of (tx + 1, tz)
     if (lane < 4) {
@@ -1167,7 +1208,7 @@ __device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fi
       if (m && ntx >= 0 && ntx < L.ntx) {
         const int nt = ntx * L.ntz + tz;
         atomicOr(bitmap + (size_t)nt * fim::kT + (lane < 2 ? fim::kT - 2 + lane : lane - 2), m);
-        active[nt] = 1;
+        atomicOr(active + (nt >> 5), 1u << (nt & 31));
       }
     }
     // z-neighbours: halo columns -2, -1 are bits 30, 31 of tile (tx, tz - 1); columns 32, 33 are bits 0, 1 of (tx, tz + 1)
@@ -1175,32 +1216,41 @@ __device__ void fim_process_tile(fim::Tile &tl, const fim::TileCtx &Cb, const fi
     const unsigned hi = ((tl.hz[2] >> lane) & 1u) | (((tl.hz[3] >> lane) & 1u) << 1);
     if (lo && tz - 1 >= 0) {
       atomicOr(bitmap + (size_t)(tile - 1) * fim::kT + lane, lo);
-      active[tile - 1] = 1;
+      atomicOr(active + ((tile - 1) >> 5), 1u << ((tile - 1) & 31));
     }
     if (hi && tz + 1 < L.ntz) {
       atomicOr(bitmap + (size_t)(tile + 1) * fim::kT + lane, hi);
-      active[tile + 1] = 1;
+      atomicOr(active + ((tile + 1) >> 5), 1u << ((tile + 1) & 31));
     }
     const unsigned left = vdirty[lane];  // walk limit reached: the tile stays active
     if (left) {
       atomicOr(bm + lane, left);
-      active[tile] = 1;
+      atomicOr(active + (tile >> 5), 1u << (tile & 31));
     }
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kFimWarps * 32, 2)
+template <int MINB, bool TMA>
+__global__ void __launch_bounds__(kFimSweepsPerCta * 32, MINB)
 k_fim_march(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict__ veln_all, const float *__restrict__ risti_c,
             BatchView bv, fim::Layout L) {
   extern __shared__ uint4 fsm4[];
-  fim::Tile *tiles = reinterpret_cast<fim::Tile *>(fsm4);
-  FimShared *ctl = reinterpret_cast<FimShared *>(tiles + kFimWarps);
-  const int ntiles = L.ntx * L.ntz;
-  unsigned short *list = reinterpret_cast<unsigned short *>(ctl + 1);
-  unsigned char *active = reinterpret_cast<unsigned char *>(list + ((ntiles + 7) & ~7));
-  const int slot = blockIdx.x;
   const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * kFimSweepsPerCta + wp;
+  if (slot >= nsw) return;
+  const int ntiles = L.ntx * L.ntz;
+  const int nwords = (ntiles + 31) >> 5, nwpad = (nwords + 3) & ~3;
+  fim::TileD *tiles = reinterpret_cast<fim::TileD *>(fsm4);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(tiles + kFimSweepsPerCta);
+  unsigned *active = reinterpret_cast<unsigned *>(bars + kFimSweepsPerCta) + wp * nwpad;  // bit per tile: relax it next round
+  fim::TileD &tl = tiles[wp];
+  unsigned long long *bar = bars + wp;
+  unsigned phase = 0;
+  if (TMA) {
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+  }
   const SweepDesc d = sw[slot];
   unsigned *T = bv.word + (size_t)slot * bv.wslot;
   unsigned *bitmap = bv.fim_bitmap + (size_t)slot * ((size_t)ntiles * fim::kT);
@@ -1220,16 +1270,16 @@ k_fim_march(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict
   C.bh = rect.w;
   C.box = reg;
   // ---- prologue: region times into the field, dirty marks for the seeds and their not-yet-alive neighbours
-  for (int i = threadIdx.x; i < ntiles; i += blockDim.x) active[i] = 0;
-  for (int i = threadIdx.x; i < C.bw * C.bh; i += blockDim.x) {
+  for (int i = lane; i < nwpad; i += 32) active[i] = 0;
+  for (int i = lane; i < C.bw * C.bh; i += 32) {
     const int st = reg[2 * i + 1];
     if (st >= 0) {
       const int bx = i / C.bh, bz = i - bx * C.bh;
       T[L.at(C.bx0 + bx, C.bz0 + bz)] = (unsigned)reg[2 * i];
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C.bw * C.bh; i += blockDim.x) {
+  __syncwarp();
+  for (int i = lane; i < C.bw * C.bh; i += 32) {
     if (reg[2 * i + 1] <= 0) continue;
     const int bx = i / C.bh, bz = i - bx * C.bh;
 #pragma unroll
@@ -1238,39 +1288,46 @@ k_fim_march(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict
       const int gx = C.bx0 + ex, gz = C.bz0 + ez;
       if (gx < 0 || gx >= C.nnx || gz < 0 || gz >= C.nnz) continue;
       if (ex >= 0 && ex < C.bw && ez >= 0 && ez < C.bh && reg[2 * (ex * C.bh + ez) + 1] == 0) continue;
-      const int tx = gx / fim::kT, tz = gz / fim::kT;
-      atomicOr(bitmap + (size_t)(tx * L.ntz + tz) * fim::kT + (gx - tx * fim::kT), 1u << (gz - tz * fim::kT));
-      active[tx * L.ntz + tz] = 1;
+      const int tx = gx / fim::kT, tz = gz / fim::kT, nt = tx * L.ntz + tz;
+      atomicOr(bitmap + (size_t)nt * fim::kT + (gx - tx * fim::kT), 1u << (gz - tz * fim::kT));
+      atomicOr(active + (nt >> 5), 1u << (nt & 31));
     }
   }
-  __syncthreads();
-  // ---- rounds: every active tile once per round
-  int guard = 0;
-  for (;;) {
-    if (threadIdx.x == 0) {
-      ctl->nlist = 0;
-      ctl->next = 0;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < ntiles; i += blockDim.x)
-      if (active[i]) {
-        active[i] = 0;
-        list[atomicAdd(&ctl->nlist, 1)] = (unsigned short)i;
+  __syncwarp();
+  // ---- rounds: every tile that was active when the round started, in index order
+  const int guard_max = 64 * (L.ntx + L.ntz) + 1024;
+  for (int round = 0;; round++) {
+    unsigned snap[kFimMaxWordsPerLane];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < kFimMaxWordsPerLane; j++) {
+      const int wi = j * 32 + lane;
+      snap[j] = 0;
+      if (wi < nwords) {
+        snap[j] = active[wi];
+        active[wi] = 0;
       }
-    __syncthreads();
-    const int nlist = ctl->nlist;
-    if (nlist == 0) break;
-    for (;;) {
-      int k = 0;
-      if (lane == 0) k = atomicAdd(&ctl->next, 1);
-      k = __shfl_sync(kFull, k, 0);
-      if (k >= nlist) break;
-      fim_process_tile(tiles[wp], C, L, (int)list[k], T, bitmap, active, vel, risti_c, d.isx - 1, d.isz - 1, lane);
+      any |= snap[j] != 0;
     }
-    __syncthreads();
-    if (++guard > 64 * (L.ntx + L.ntz) + 1024) {  // no fixed point (cannot happen for a causal rule): report instead of hanging
-      if (threadIdx.x == 0) sw[slot].status = DSURF_ERR_HEAP;
+    __syncwarp();
+    if (!__any_sync(kFull, any)) break;
+    if (round > guard_max) {  // no fixed point (cannot happen for a causal rule): report instead of hanging
+      if (lane == 0) sw[slot].status = DSURF_ERR_HEAP;
       break;
+    }
+#pragma unroll
+    for (int j = 0; j < kFimMaxWordsPerLane; j++) {
+      unsigned lanes = __ballot_sync(kFull, snap[j] != 0);
+      while (lanes) {
+        const int src = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        unsigned w = __shfl_sync(kFull, snap[j], src);
+        while (w) {
+          const int b = __ffs(w) - 1;
+          w &= w - 1;
+          fim_process_tile<TMA>(tl, C, L, (j * 32 + src) * 32 + b, T, bitmap, active, vel, risti_c, d.isx - 1, d.isz - 1, lane, bar, phase);
+        }
+      }
     }
   }
 }
@@ -1353,8 +1410,7 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
   const size_t smem = (size_t)kWarpsPerBlock * V3<16>::NG * (V3<16>::HS + kScr) * sizeof(int2);
   const fim::Layout L = fim::make_layout(g.nnx, g.nnz);
   const int ntiles = L.ntx * L.ntz;
-  const size_t fsm = (size_t)kFimWarps * sizeof(fim::Tile) + sizeof(FimShared) + (size_t)((ntiles + 7) & ~7) * sizeof(unsigned short) +
-                     (size_t)((ntiles + 15) & ~15);
+  const size_t fsm = (size_t)kFimSweepsPerCta * (sizeof(fim::TileD) + sizeof(unsigned long long) + (size_t)((((ntiles + 31) >> 5) + 3) & ~3) * sizeof(unsigned));
   static bool attr = false;
   if (!attr) {
     DS_CUDA(cudaFuncSetAttribute(k_eikonal3<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1362,7 +1418,11 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     DS_CUDA(cudaFuncSetAttribute(k_refine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DS_CUDA(cudaFuncSetAttribute(k_march_lps, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DS_CUDA(cudaFuncSetAttribute(k_march_lps, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-    DS_CUDA(cudaFuncSetAttribute(k_fim_march, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DS_CUDA(cudaFuncSetAttribute(k_fim_march<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DS_CUDA(cudaFuncSetAttribute(k_fim_march<6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DS_CUDA(cudaFuncSetAttribute(k_fim_march<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DS_CUDA(cudaFuncSetAttribute(k_fim_march<6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DS_CUDA(cudaFuncSetAttribute(k_fim_march<5, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   if (mode == kEikExact16) {
@@ -1378,19 +1438,37 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
   }
   DS_CUDA(cudaMemsetAsync(bv.word, 0xFF, (size_t)nsw * bv.wslot * sizeof(unsigned), st));  // every node (and the frame) far
   if (mode == kEikFim) {
-    if (ntiles > 65535 || fsm > 227 * 1024) {
-      set_error(__FILE__, __LINE__, "fast-iterative eikonal: grid too large for the per-sweep tile list");
+    if (ntiles > kFimMaxWordsPerLane * 32 * 32) {
+      set_error(__FILE__, __LINE__, "fast-iterative eikonal: grid too large for the per-sweep tile bitmask (5120 tiles)");
       return DSURF_ERR_BAD_ARG;
     }
     static size_t fsm_set = 0;
     if (fsm > fsm_set) {
-      DS_CUDA(cudaFuncSetAttribute(k_fim_march, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      DS_CUDA(cudaFuncSetAttribute(k_fim_march<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      DS_CUDA(cudaFuncSetAttribute(k_fim_march<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      DS_CUDA(cudaFuncSetAttribute(k_fim_march<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      DS_CUDA(cudaFuncSetAttribute(k_fim_march<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      DS_CUDA(cudaFuncSetAttribute(k_fim_march<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
       fsm_set = fsm;
     }
+    // resident CTAs per SM the kernel is compiled for (4 sweeps each): 6 = 80 registers per thread (default), 4 = 128, 8 = 64
+    static const int minb = getenv("DSURF_FIM_MINB") ? atoi(getenv("DSURF_FIM_MINB")) : 6;
     DS_CUDA(cudaMemsetAsync(bv.fim_bitmap, 0, (size_t)nsw * ntiles * fim::kT * sizeof(unsigned), st));
     k_refine<16><<<grid3, nt, smem, st>>>(g, sw, nsw, d_velv_all, bv, false);
     k_fim_start<<<(nsw + 127) / 128, 128, 0, st>>>(g, sw, nsw, d_veln_all, d_risti, bv);
-    k_fim_march<<<nsw, kFimWarps * 32, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
+    const int fgrid = (nsw + kFimSweepsPerCta - 1) / kFimSweepsPerCta, fnt = kFimSweepsPerCta * 32;
+    // tile rows through the TMA engine (cp.async.bulk + mbarrier) or with plain 16-byte loads (DSURF_FIM_TMA=0)
+    static const bool tma = !(getenv("DSURF_FIM_TMA") && atoi(getenv("DSURF_FIM_TMA")) == 0);
+    if (minb == 4)
+      k_fim_march<4, false><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
+    else if (minb == 8)
+      k_fim_march<8, false><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
+    else if (minb == 5)
+      k_fim_march<5, true><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
+    else if (tma)
+      k_fim_march<6, true><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
+    else
+      k_fim_march<6, false><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
     DS_CUDA(cudaGetLastError());
     if (launches) *launches += 3;
     return DSURF_OK;

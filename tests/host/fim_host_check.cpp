@@ -12,6 +12,7 @@
 #include <cstring>
 #include <random>
 #include <vector>
+#define DSURF_FIM_CROSSCHECK 1
 #include "../../dsurftomo_b200/csrc/eik_fim.cuh"
 #include "../../oracle/fmm.h"
 
@@ -102,7 +103,7 @@ struct HostSweep {
         for (int x = 0; x < kT; x++)
           if (zs[x] >= 0) {
             st.evals++;
-            changed |= relax_node(tl, C, x, zs[x]);
+            changed |= relax_node(tl, C, x, zs[x], tl.slow[x * kT + zs[x]]);
           }
       }
     }
@@ -399,7 +400,9 @@ int main(int argc, char **argv) {
          a.nnx, rough, nsrc, sweeps_mis, tot_mis, tot_nodes, (double)tot_mis / tot_nodes, worst, unreached, rays, rays_pattern, rays_val, worst_dt,
          (double)tot.rounds / nsrc, (double)tot.activations / nsrc, (double)tot.walks / nsrc, (double)tot.steps / nsrc, (double)tot.evals / tot_nodes);
   printf("start-up pops per sweep: %.1f\n", (double)g_start_pops / nsrc);
-  const bool ok = unreached == 0 && worst <= 1e-5 && (double)tot_mis / tot_nodes <= 5e-2 && rays_pattern == 0;
+  printf("rule cross-check: evaluations=%ld cached_vs_plain_mismatch=%ld handed_to_generic=%ld (%.3f %%)\n", dsurf::fim::g_cross_total,
+         dsurf::fim::g_cross_mismatch, dsurf::fim::g_generic_calls, 100.0 * dsurf::fim::g_generic_calls / std::max(1L, dsurf::fim::g_cross_total));
+  const bool ok = dsurf::fim::g_cross_mismatch == 0 && unreached == 0 && worst <= 1e-5 && (double)tot_mis / tot_nodes <= 5e-2 && rays_pattern == 0;
   printf(ok ? "FIM HOST CHECK OK\n" : "FIM HOST CHECK FAILED\n");
   return ok ? 0 : 1;
 }
