@@ -241,13 +241,21 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    plan = api.Plan(pb)
-    for t in range(4):
-        if (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)[t] > 0:
-            plan.set_dispersion(t, pv4[t], *sen12[3 * t:3 * t + 3])
-        elif t in (0, 2):
-            plan.set_dispersion(t, pv4[t], None, None, None)
-    plan.finalize_dispersion()
+    MODE = args.eikonal
+
+    def make_plan(mode):
+        prev = api.set_eikonal_mode(mode)
+        plan = api.Plan(pb)
+        api.set_eikonal_mode(prev)
+        for t in range(4):
+            if (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)[t] > 0:
+                plan.set_dispersion(t, pv4[t], *sen12[3 * t:3 * t + 3])
+            elif t in (0, 2):
+                plan.set_dispersion(t, pv4[t], None, None, None)
+        plan.finalize_dispersion()
+        return plan
+
+    plan = make_plan(MODE)
     nb = len(blocks)
 
     def block_of(step):
@@ -258,108 +266,133 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         lo, hi = ddist.shard_range(b1 - b0, rank, world)
         return b0 + lo, b0 + hi
 
-    # ---------------- timed region 1: device-resident sweep stage + the NCCL gather of predicted times and COO row
-    # blocks to every rank (CUDA events on the launching stream, max over ranks)
-    sampler = ClockSampler(local)
-    dev_ms, eik_ms, gat_ms, nsw_local, launches, wall, launches_eik, nrays_local = 0.0, 0.0, 0.0, 0, 0, 0.0, 0, 0
-    stage = dict(eikonal_ms=0.0, rays_ms=0.0, assembly_ms=0.0)
-    nar_total, digest = 0, None
-    for s in range(args.warmup + args.steps):
-        if s == args.warmup:
-            barrier()
-            if rank == 0:
-                sampler.start()
-            w0 = time.perf_counter()
-        g0, g1 = block_of(s)
-        plan.reset_rows()
-        plan.sweeps(g0, g1)
-        if comm is not None:
-            nar_total = plan.allgather(comm, want_coo=True)
-        else:
-            nar_total = plan.nar
-        if s >= args.warmup:
-            r0_, r1_ = ddist.rows_of_gathers(pb, g0, g1)
-            nrays_local += r1_ - r0_
-            tm = plan.timings()
-            dev_ms += tm["total_ms"] + (plan.gather_ms if comm is not None else 0.0)
-            gat_ms += plan.gather_ms if comm is not None else 0.0
-            eik_ms += tm["eikonal_ms"]
-            nsw_local += tm["sweeps"]
-            launches += tm["launches"]
-            launches_eik += tm["eikonal_launches"]
-            for k in stage:
-                stage[k] += tm[k]
-    barrier()
-    wall = time.perf_counter() - w0
-    clocks = sampler.stop() if rank == 0 else None
-    digest = plan.digest(gathered=comm is not None)  # equal on 1 and on N GPUs <=> identical COO in identical order
-    t_max_ms = maxreduce(dev_ms)
-    nsw_total = sumreduce(nsw_local)
-    value = nsw_total / (t_max_ms / 1e3)
-    Nc = ((pb.nx - 3) * 8 + 1) * ((pb.ny - 3) * 8 + 1)
-    b_sweep = 8 * (Nc + 129 * 129)  # veln read + ttn write, coarse + refined
-    peak, peak_src = peaks()
-    achieved = b_sweep * nsw_local / (eik_ms / 1e3) / 1e9
-    n_eik_launches = max(1, int(round(launches_eik)))
-    mt = measured_traffic()
-    traffic = None
-    lps = os.environ.get("DSURF_EIKONAL_LPS") is not None
-    if mt and pb.nx == 131 and not lps:  # measured at cfg 3 only, default kernel
-        traffic = mt["eikonal"]["dram_bytes_per_sweep"] * nsw_local / n_eik_launches
-    roofline = dict(bound="hbm", kernel=("k_refine<16> + k_march_lps" if lps else "k_eikonal3<16> (+ node-state fill)"),
-                    achieved=achieved, peak=peak, unit="GB/s",
-                    frac=achieved / peak, traffic=traffic, peak_source=peak_src,
-                    algorithmic_bytes_per_sweep=b_sweep, algorithmic_bytes_per_launch=b_sweep * nsw_local / n_eik_launches,
-                    launches=n_eik_launches, avg_launch_ms=eik_ms / n_eik_launches,
-                    traffic_source=(mt["eikonal"]["source"] if traffic else None),
-                    note="exact-order FMM replay: bound by dependent scattered accesses (issue slots of the serial heap "
-                         "work, then DRAM sector rate), not by the algorithmic bytes; DRAM traffic ~250x B_sweep; see "
-                         "DESIGN.md section 4")
-
-    # ---------------- timed region 2: end to end through the host-buffer API (H2D + compute + gather + D2H on rank 0)
-    cap = int(nar_total * (1.05 if args.step_mode == "stage" else 1.6)) + 1024
-    pin = None
-    if rank == 0:
-        pin = dict(row=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
-                   col=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
-                   rw=torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy(),
-                   dsurf=torch.empty(max(pb.dall, 1), dtype=torch.float32, pin_memory=True).numpy())
-    h2d = pb.vsf.nbytes + sum(a.nbytes for a in pv4) + sum(a.nbytes for a in sen12 if a is not None) + \
-        pb.scxf.nbytes * 2 + pb.rcxf.nbytes * 2
-    e2e_steps = max(1, min(args.steps, 5))
-    e2e_t, e2e_sw, d2h = 0.0, 0, 0
-    barrier()
-    for s in range(e2e_steps):
-        g0, g1 = block_of(args.warmup + s)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        plan.set_model(pb.vsf)                                   # H2D: model
-        for t in range(4):                                       # H2D: this step's maps + kernels
-            if (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)[t] > 0:
-                plan.set_dispersion(t, pv4[t], *sen12[3 * t:3 * t + 3])
-            elif t in (0, 2):
-                plan.set_dispersion(t, pv4[t], None, None, None)
-        plan.finalize_dispersion()
-        plan.reset_rows()
-        plan.sweeps(g0, g1)
-        if comm is not None:
-            ntot = plan.allgather(comm, want_coo=True)
-            if rank == 0:                                        # D2H: the caller's full (rw, iw, col) + predicted times
-                lib_ = api.lib()
-                import ctypes as C
-                api.check(lib_.dsurf_plan_download_gathered(plan.h, api.ptr(pin["row"], C.c_int), api.ptr(pin["rw"], C.c_float),
-                                                            api.ptr(pin["col"], C.c_int)), "download_gathered")
-                api.check(lib_.dsurf_plan_download(plan.h, None, None, None, api.ptr(pin["dsurf"], C.c_float), None),
-                          "download_dsurf")
-        else:
-            ntot = plan.download(out=pin)["nar"]                 # D2H: predicted times + COO rows
-        torch.cuda.synchronize()
+    def measure(plan, mode, want_clocks=True, nwarm=None, nsteps=None):
+        """timed regions 1 (device-resident) and 2 (host buffers) of the sweep stage for one eikonal pipeline"""
+        nwarm = args.warmup if nwarm is None else nwarm
+        nsteps = args.steps if nsteps is None else nsteps
+        # ---------------- timed region 1: device-resident sweep stage + the NCCL gather of predicted times and COO row
+        # blocks to every rank (CUDA events on the launching stream, max over ranks)
+        sampler = ClockSampler(local) if want_clocks else None
+        dev_ms, eik_ms, gat_ms, nsw_local, launches, wall, launches_eik, nrays_local = 0.0, 0.0, 0.0, 0, 0, 0.0, 0, 0
+        stage = dict(eikonal_ms=0.0, rays_ms=0.0, assembly_ms=0.0)
+        nar_total, digest = 0, None
+        for s in range(nwarm + nsteps):
+            if s == nwarm:
+                barrier()
+                if rank == 0 and sampler is not None:
+                    sampler.start()
+                w0 = time.perf_counter()
+            g0, g1 = block_of(s)
+            plan.reset_rows()
+            plan.sweeps(g0, g1)
+            if comm is not None:
+                nar_total = plan.allgather(comm, want_coo=True)
+            else:
+                nar_total = plan.nar
+            if s >= nwarm:
+                r0_, r1_ = ddist.rows_of_gathers(pb, g0, g1)
+                nrays_local += r1_ - r0_
+                tm = plan.timings()
+                dev_ms += tm["total_ms"] + (plan.gather_ms if comm is not None else 0.0)
+                gat_ms += plan.gather_ms if comm is not None else 0.0
+                eik_ms += tm["eikonal_ms"]
+                nsw_local += tm["sweeps"]
+                launches += tm["launches"]
+                launches_eik += tm["eikonal_launches"]
+                for k in stage:
+                    stage[k] += tm[k]
         barrier()
-        e2e_t += time.perf_counter() - t0
-        e2e_sw += plan.timings()["sweeps"]
-        d2h = 12 * ntot + 4 * pb.dall
-    e2e_tmax = maxreduce(e2e_t)
-    e2e_value = sumreduce(e2e_sw) / e2e_tmax
+        wall = time.perf_counter() - w0
+        clocks = sampler.stop() if (rank == 0 and sampler is not None) else None
+        digest = plan.digest(gathered=comm is not None)  # equal on 1 and on N GPUs <=> identical COO in identical order
+        t_max_ms = maxreduce(dev_ms)
+        nsw_total = sumreduce(nsw_local)
+        value = nsw_total / (t_max_ms / 1e3)
+        Nc = ((pb.nx - 3) * 8 + 1) * ((pb.ny - 3) * 8 + 1)
+        b_sweep = 8 * (Nc + 129 * 129)  # SURVEY.md section 8(d): veln read + ttn write, coarse + refined
+        peak, peak_src = peaks()
+        achieved = b_sweep * nsw_local / (eik_ms / 1e3) / 1e9
+        n_eik_launches = max(1, int(round(launches_eik)))
+        mt = measured_traffic()
+        traffic = None
+        traffic_src = None
+        if mt and pb.nx == 131 and mode == "exact":  # measured at cfg 3 only
+            traffic = mt["eikonal"]["dram_bytes_per_sweep"] * nsw_local / n_eik_launches
+            traffic_src = mt["eikonal"]["source"]
+        if mt and pb.nx == 131 and mode == "fim" and "eikonal_fim" in mt:
+            traffic = mt["eikonal_fim"]["dram_bytes_per_sweep"] * nsw_local / n_eik_launches
+            traffic_src = mt["eikonal_fim"]["source"]
+        kname = {"exact": "k_eikonal3<16> (+ node-state fill)", "lps": "k_refine<16> + k_march_lps",
+                 "fim": "k_fim_march (+ k_refine<16>, k_fim_start, field fill)"}[mode]
+        note = {"fim": "block-level fast-iterative sweep: ~50 warp instructions per node (fp32 IEEE sqrt/div chains), issue-bound; "
+                       "DRAM traffic ~2x B_sweep (tiles are re-read from L2); see DESIGN.md section 4",
+                "lps": "exact-order FMM replay, lane per sweep: latency-bound",
+                "exact": "exact-order FMM replay: bound by dependent scattered accesses (issue slots of the serial heap "
+                         "work, then DRAM sector rate), not by the algorithmic bytes; DRAM traffic ~250x B_sweep; see "
+                         "DESIGN.md section 4"}[mode]
+        roofline = dict(bound="hbm", kernel=kname,
+                        achieved=achieved, peak=peak, unit="GB/s",
+                        frac=achieved / peak, traffic=traffic, peak_source=peak_src,
+                        algorithmic_bytes_per_sweep=b_sweep, algorithmic_bytes_per_launch=b_sweep * nsw_local / n_eik_launches,
+                        launches=n_eik_launches, avg_launch_ms=eik_ms / n_eik_launches,
+                        traffic_source=traffic_src, note=note)
+
+        # ---------------- timed region 2: end to end through the host-buffer API (H2D + compute + gather + D2H on rank 0)
+        cap = int(nar_total * (1.05 if args.step_mode == "stage" else 1.6)) + 1024
+        pin = None
+        if rank == 0:
+            pin = dict(row=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+                       col=torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+                       rw=torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy(),
+                       dsurf=torch.empty(max(pb.dall, 1), dtype=torch.float32, pin_memory=True).numpy())
+        h2d = pb.vsf.nbytes + sum(a.nbytes for a in pv4) + sum(a.nbytes for a in sen12 if a is not None) + \
+            pb.scxf.nbytes * 2 + pb.rcxf.nbytes * 2
+        e2e_steps = max(1, min(nsteps, 5))
+        e2e_t, e2e_sw, d2h = 0.0, 0, 0
+        barrier()
+        for s in range(e2e_steps):
+            g0, g1 = block_of(nwarm + s)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            plan.set_model(pb.vsf)                                   # H2D: model
+            for t in range(4):                                       # H2D: this step's maps + kernels
+                if (pb.kmaxRc, pb.kmaxRg, pb.kmaxLc, pb.kmaxLg)[t] > 0:
+                    plan.set_dispersion(t, pv4[t], *sen12[3 * t:3 * t + 3])
+                elif t in (0, 2):
+                    plan.set_dispersion(t, pv4[t], None, None, None)
+            plan.finalize_dispersion()
+            plan.reset_rows()
+            plan.sweeps(g0, g1)
+            if comm is not None:
+                ntot = plan.allgather(comm, want_coo=True)
+                if rank == 0:                                        # D2H: the caller's full (rw, iw, col) + predicted times
+                    lib_ = api.lib()
+                    import ctypes as C
+                    api.check(lib_.dsurf_plan_download_gathered(plan.h, api.ptr(pin["row"], C.c_int), api.ptr(pin["rw"], C.c_float),
+                                                                api.ptr(pin["col"], C.c_int)), "download_gathered")
+                    api.check(lib_.dsurf_plan_download(plan.h, None, None, None, api.ptr(pin["dsurf"], C.c_float), None),
+                              "download_dsurf")
+            else:
+                ntot = plan.download(out=pin)["nar"]                 # D2H: predicted times + COO rows
+            torch.cuda.synchronize()
+            barrier()
+            e2e_t += time.perf_counter() - t0
+            e2e_sw += plan.timings()["sweeps"]
+            d2h = 12 * ntot + 4 * pb.dall
+        e2e_tmax = maxreduce(e2e_t)
+        e2e_value = sumreduce(e2e_sw) / e2e_tmax
+
+        return dict(value=value, t_max_ms=t_max_ms, roofline=roofline, e2e_value=e2e_value, e2e_steps=e2e_steps, h2d=h2d,
+                    d2h=d2h, launches=launches, clocks=clocks, stage=stage, gat_ms=gat_ms, nar_total=nar_total, digest=digest,
+                    wall=wall, nrays_local=nrays_local, cap=cap)
+
+    M = measure(plan, MODE)
+    value, t_max_ms, roofline, e2e_value, e2e_steps, h2d, d2h = (M[k] for k in ("value", "t_max_ms", "roofline", "e2e_value",
+                                                                               "e2e_steps", "h2d", "d2h"))
+    launches, clocks, stage, gat_ms, nar_total, digest, wall, nrays_local, cap = (M[k] for k in (
+        "launches", "clocks", "stage", "gat_ms", "nar_total", "digest", "wall", "nrays_local", "cap"))
+    peak, peak_src = peaks()
+    mt = measured_traffic()
 
     # ---------------- LSMR on the FULL system of the step (every data row + every smoothing row, main.f90:418-489),
     # row-partitioned over the ranks exactly as the rows were produced; built on the device from the plans' COO
@@ -439,6 +472,26 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
         if disp is not None:
             cpu["dispersion"] = cpu_dispersion_sample(pb, cores)
 
+    # ---------------- the other eikonal pipeline on the same steps: the block-level fast-iterative sweep (north_star's
+    # design, not bit-exact: profiles/r02_fim_parity.md) next to the exact-order kernel, or the other way round
+    other = None
+    if args.both and args.step_mode == "stage":
+        om = "fim" if MODE != "fim" else "exact"
+        plan.close()
+        plan = make_plan(om)
+        M2 = measure(plan, om, want_clocks=False, nwarm=min(args.warmup, 3 if om == "fim" else 1),
+                     nsteps=max(1, min(args.steps, 3 if om == "fim" else 1)))
+        if rank == 0:
+            other = dict(pipeline=om, value=M2["value"], unit="sweeps/s", ms_per_step=M2["t_max_ms"] / max(1, min(args.steps, 3 if om == "fim" else 1)),
+                         e2e=dict(value=M2["e2e_value"], unit="sweeps/s", h2d_bytes_per_step=int(M2["h2d"]),
+                                  d2h_bytes_per_step=int(M2["d2h"]), steps=M2["e2e_steps"]),
+                         roofline=M2["roofline"], gpu_launches=int(M2["launches"]),
+                         stage_ms_per_step={k: v / max(1, min(args.steps, 3 if om == "fim" else 1)) for k, v in M2["stage"].items()},
+                         coo=dict(nar=int(M2["nar_total"]), digest=f"{M2['digest'][0]:016x}"),
+                         parity=("travel times bit-identical to the reference" if om == "exact" else
+                                 "iterates the reference's own update rule: <= 2.2e-6 relative on travel times at 1025^2 (1.5 % of "
+                                 "the nodes, last bits), 0.7 % of the rays change their B-spline vertex pattern at 1025^2, none "
+                                 "at <= 257^2; profiles/r02_fim_parity.md"))
     if rank == 0:
         cfg = make_config(pb, world, args.step_mode)
         out = dict(metric=METRIC, value=value, unit="sweeps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -460,14 +513,20 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
                              rows_per_s=(nrays_local / (stage["assembly_ms"] / 1e3) if stage["assembly_ms"] > 0 else None),
                              note="rank 0: receiver times + ray back-trace (k_rays) and Frechet row assembly, rays per second "
                                   "of their own stage time (SURVEY.md 8d: latency-bound gathers, no HBM fraction quoted)"),
-                   lsmr=lsmr, dispersion=disp, impl="b200")
+                   lsmr=lsmr, dispersion=disp, impl="b200", eikonal_pipeline=MODE,
+                   eikonal_pipeline_note=("exact: the reference's heap pop order replayed, travel times bit-identical (library "
+                                          "default)" if MODE == "exact" else "fim: block-level fast-iterative sweep, not bit-exact, "
+                                          "see other_pipeline.parity" if MODE == "fim" else MODE),
+                   other_pipeline=other)
     plan.close()
     # ---------------- e2e through dsurf_calsurfg itself (K1 included), host buffers in and out: the call a Fortran
     # main program makes (main.f90:355-359).  N = 1 only; its own plan needs the memory the bench plan just released.
     if rank == 0 and world == 1 and args.calsurfg_e2e and args.step_mode == "stage":
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        prev_mode = api.set_eikonal_mode(MODE)
         res = api.CalSurfG(pb, maxnar=cap)
+        api.set_eikonal_mode(prev_mode)
         dt = time.perf_counter() - t0
         out["e2e_calsurfg"] = dict(value=out["config"]["sweeps_per_step"] / dt, unit="sweeps/s", seconds=dt, steps=1,
                                    nar=int(res["nar"]),
@@ -511,6 +570,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dispersion", dest="dispersion", action="store_false")
     ap.add_argument("--no-calsurfg-e2e", dest="calsurfg_e2e", action="store_false")
+    ap.add_argument("--eikonal", default=os.environ.get("DSURF_EIKONAL", "exact"), choices=["exact", "lps", "fim"],
+                    help="eikonal pipeline of the headline numbers (library default: exact)")
+    ap.add_argument("--no-both", dest="both", action="store_false",
+                    help="skip the second pass with the other eikonal pipeline (other_pipeline key)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference" and rank != 0:
