@@ -108,10 +108,14 @@ class ClockSampler:
 
 
 def measured_traffic():
-    """DRAM bytes measured with ncu (profiles/r01_traffic.json): per sweep of the eikonal kernel at cfg 3 and
-    per non-zero per LSMR iteration.  Scaled by the units of one launch in the roofline objects."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else None
+    """DRAM bytes measured with ncu (profiles/r02_traffic.json, falling back to r01): per sweep of the eikonal kernels at
+    cfg 3 (exact and fast-iterative) and per non-zero per LSMR iteration.  Scaled by the units of one launch in the
+    roofline objects."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))
+    return None
 
 
 def lsmr_bytes(nnz, m, n):
