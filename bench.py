@@ -403,9 +403,7 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
     lsmr = None
     if args.lsmr_iters > 0 and args.step_mode == "stage":
         g0, g1 = block_of(0)
-        if comm is None:
-            plan.reset_rows()
-            plan.sweeps(g0, g1)      # fresh, unscaled rows (the e2e loop left them unscaled too; keep it explicit)
+        # the last end-to-end step left this rank's rows of the stage on the device, unscaled: LSMR is built from them
         t0 = time.perf_counter()
         sysl = api.LsmrSystem.from_plan_shard(plan, rank, world)
         t_build = time.perf_counter() - t0

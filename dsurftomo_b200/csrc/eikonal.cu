@@ -1109,6 +1109,91 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 constexpr int kFimSweepsPerCta = 4;
 constexpr int kFimMaxWordsPerLane = 5;  // tile-activity bitmask: up to 5 * 32 * 32 = 5120 tiles (71 x 71: 2272^2 nodes)
 
+// ---- tile load: 36 rows of 40 words (16-byte aligned) into shared memory, far -> +inf, region nodes alive before the pass
+// get the flag; risti column factors, the tile's dirty words, cleared halo marks
+template <bool TMA>
+__device__ __forceinline__ void fim_tile_load(fim::TileD &tl, const fim::TileCtx &C, const fim::Layout L, const unsigned *T,
+                                              const float *risti_c, unsigned mydirty, int lane, unsigned long long *bar,
+                                              unsigned &phase) {
+  const bool touches = C.gx0 - fim::kHX < C.bx0 + C.bw && C.gx0 + fim::kT + fim::kHX > C.bx0 &&
+                       C.gz0 - fim::kHZ < C.bz0 + C.bh && C.gz0 + fim::kT + fim::kHZ > C.bz0;
+  const uint4 *src = reinterpret_cast<const uint4 *>(T + (size_t)C.gx0 * L.pitch + C.gz0);  // row gx0 - kHX, column gz0 - kHZ
+  constexpr int kVecRow = fim::kPitch / 4;
+  if (TMA) {
+    // the 36 rows (160 bytes each, 16-byte aligned) go through the TMA engine; one mbarrier per tile buffer counts the bytes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the tile buffer
+    if (lane == 0) mbar_expect_tx(bar, fim::kRows * fim::kPitch * 4);
+    __syncwarp();
+    for (int r = lane; r < fim::kRows; r += 32)
+      bulk_g2s(tl.t + r * fim::kPitch, src + (size_t)r * (L.pitch / 4), fim::kPitch * 4, bar);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  }
+  for (int i = lane; i < fim::kRows * kVecRow; i += 32) {
+    const int r = i / kVecRow, c4 = i - r * kVecRow;
+    uint4 v = TMA ? *reinterpret_cast<const uint4 *>(tl.t + r * fim::kPitch + 4 * c4) : src[(size_t)r * (L.pitch / 4) + c4];
+    v.x = (int)v.x < 0 ? fim::kInf : v.x;
+    v.y = (int)v.y < 0 ? fim::kInf : v.y;
+    v.z = (int)v.z < 0 ? fim::kInf : v.z;
+    v.w = (int)v.w < 0 ? fim::kInf : v.w;
+    if (touches) {
+      const int bx = C.gx0 + r - fim::kHX - C.bx0, bz = C.gz0 + 4 * c4 - fim::kHZ - C.bz0;
+      if (bx >= 0 && bx < C.bw) {
+        unsigned *e = &v.x;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (bz + k >= 0 && bz + k < C.bh && C.box[2 * (bx * C.bh + bz + k) + 1] == 0) e[k] |= fim::kInit;
+      }
+    }
+    *reinterpret_cast<uint4 *>(tl.t + r * fim::kPitch + 4 * c4) = v;
+  }
+  const int gx = C.gx0 + lane;
+  tl.risti[lane] = gx < C.nnx ? __ldg(risti_c + gx) : 0.0f;
+  tl.dirty[lane] = mydirty;
+  if (lane < 4) tl.hx[lane] = 0;
+  if (lane >= 4 && lane < 8) tl.hz[lane - 4] = 0;
+}
+
+// ---- tile store: the interior (coalesced rows) if anything changed, then the marks for the neighbour tiles
+__device__ __forceinline__ void fim_tile_store(fim::TileD &tl, const fim::TileCtx &C, const fim::Layout L, int tile, unsigned *T,
+                                               unsigned *bitmap, unsigned *active, int lane, bool changed) {
+  const int tx = tile / L.ntz, tz = tile - tx * L.ntz;
+  if (changed) {
+    const int gz = C.gz0 + lane;
+    for (int x = 0; x < fim::kT; x++) {
+      const int gx = C.gx0 + x;
+      const unsigned w = *tl.at(x, lane);
+      if (gx < C.nnx && gz < C.nnz && (int)w >= 0) T[L.at(gx, gz)] = (w == fim::kInf) ? fim::kFarG : w;
+    }
+  }
+  // x-neighbours: halo rows -2, -1 are rows 30, 31 of tile (tx - 1, tz); rows 32, 33 are rows 0, 1 of (tx + 1, tz)
+  if (lane < 4) {
+    const unsigned m = tl.hx[lane];
+    const int ntx = lane < 2 ? tx - 1 : tx + 1;
+    if (m && ntx >= 0 && ntx < L.ntx) {
+      const int nt = ntx * L.ntz + tz;
+      atomicOr(bitmap + (size_t)nt * fim::kT + (lane < 2 ? fim::kT - 2 + lane : lane - 2), m);
+      atomicOr(active + (nt >> 5), 1u << (nt & 31));
+    }
+  }
+  // z-neighbours: halo columns -2, -1 are bits 30, 31 of tile (tx, tz - 1); columns 32, 33 are bits 0, 1 of (tx, tz + 1)
+  const unsigned lo = (((tl.hz[0] >> lane) & 1u) << 30) | (((tl.hz[1] >> lane) & 1u) << 31);
+  const unsigned hi = ((tl.hz[2] >> lane) & 1u) | (((tl.hz[3] >> lane) & 1u) << 1);
+  if (lo && tz - 1 >= 0) {
+    atomicOr(bitmap + (size_t)(tile - 1) * fim::kT + lane, lo);
+    atomicOr(active + ((tile - 1) >> 5), 1u << ((tile - 1) & 31));
+  }
+  if (hi && tz + 1 < L.ntz) {
+    atomicOr(bitmap + (size_t)(tile + 1) * fim::kT + lane, hi);
+    atomicOr(active + ((tile + 1) >> 5), 1u << ((tile + 1) & 31));
+  }
+  const unsigned left = ((volatile unsigned *)tl.dirty)[lane];  // walk limit reached: the tile stays active
+  if (left) {
+    atomicOr(bitmap + (size_t)tile * fim::kT + lane, left);
+    atomicOr(active + (tile >> 5), 1u << (tile & 31));
+  }
+}
+
 // the warp relaxes one tile: load (times + halo), anti-diagonal walks, store, marks for the neighbour tiles
 template <bool TMA>
 __device__ __forceinline__ void fim_process_tile(fim::TileD &tl, const fim::TileCtx &Cb, const fim::Layout L, int tile, unsigned *T,
@@ -1122,48 +1207,7 @@ __device__ __forceinline__ void fim_process_tile(fim::TileD &tl, const fim::Tile
   fim::TileCtx C = Cb;
   C.gx0 = tx * fim::kT;
   C.gz0 = tz * fim::kT;
-  // ---- load: 36 rows of 40 words (16-byte aligned), far -> +inf, region nodes alive before the pass get the flag
-  const bool touches = C.gx0 - fim::kHX < C.bx0 + C.bw && C.gx0 + fim::kT + fim::kHX > C.bx0 &&
-                       C.gz0 - fim::kHZ < C.bz0 + C.bh && C.gz0 + fim::kT + fim::kHZ > C.bz0;
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(T + (size_t)C.gx0 * L.pitch + C.gz0);  // row gx0 - kHX, column gz0 - kHZ
-    constexpr int kVecRow = fim::kPitch / 4;
-    if (TMA) {
-      // the 36 rows (160 bytes each, 16-byte aligned) go through the TMA engine; one mbarrier per warp counts the bytes
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the tile buffer
-      if (lane == 0) mbar_expect_tx(bar, fim::kRows * fim::kPitch * 4);
-      __syncwarp();
-      for (int r = lane; r < fim::kRows; r += 32)
-        bulk_g2s(tl.t + r * fim::kPitch, src + (size_t)r * (L.pitch / 4), fim::kPitch * 4, bar);
-      mbar_wait(bar, phase);
-      phase ^= 1u;
-    }
-    for (int i = lane; i < fim::kRows * kVecRow; i += 32) {
-      const int r = i / kVecRow, c4 = i - r * kVecRow;
-      uint4 v = TMA ? *reinterpret_cast<const uint4 *>(tl.t + r * fim::kPitch + 4 * c4) : src[(size_t)r * (L.pitch / 4) + c4];
-      v.x = (int)v.x < 0 ? fim::kInf : v.x;
-      v.y = (int)v.y < 0 ? fim::kInf : v.y;
-      v.z = (int)v.z < 0 ? fim::kInf : v.z;
-      v.w = (int)v.w < 0 ? fim::kInf : v.w;
-      if (touches) {
-        const int bx = C.gx0 + r - fim::kHX - C.bx0, bz = C.gz0 + 4 * c4 - fim::kHZ - C.bz0;
-        if (bx >= 0 && bx < C.bw) {
-          unsigned *e = &v.x;
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (bz + k >= 0 && bz + k < C.bh && C.box[2 * (bx * C.bh + bz + k) + 1] == 0) e[k] |= fim::kInit;
-        }
-      }
-      *reinterpret_cast<uint4 *>(tl.t + r * fim::kPitch + 4 * c4) = v;
-    }
-  }
-  {
-    const int gx = C.gx0 + lane;
-    tl.risti[lane] = gx < C.nnx ? __ldg(risti_c + gx) : 0.0f;
-    tl.dirty[lane] = mydirty;
-    if (lane < 4) tl.hx[lane] = 0;
-    if (lane >= 4 && lane < 8) tl.hz[lane - 4] = 0;
-  }
+  fim_tile_load<TMA>(tl, C, L, T, risti_c, mydirty, lane, bar, phase);
   __syncwarp();
   // ---- relax: anti-diagonal walks (lane = tile row), first away from the source
   const int sx0 = (C.gx0 + fim::kT / 2 >= srcx) ? 1 : -1, sz0 = (C.gz0 + fim::kT / 2 >= srcz) ? 1 : -1;
@@ -1191,43 +1235,7 @@ __device__ __forceinline__ void fim_process_tile(fim::TileD &tl, const fim::Tile
     }
   }
   changed = __any_sync(kFull, changed);
-  // ---- store the interior (coalesced rows), then hand the marks to the neighbour tiles
-  if (changed) {
-    const int gz = C.gz0 + lane;
-    for (int x = 0; x < fim::kT; x++) {
-      const int gx = C.gx0 + x;
-      const unsigned w = *tl.at(x, lane);
-      if (gx < C.nnx && gz < C.nnz && (int)w >= 0) T[L.at(gx, gz)] = (w == fim::kInf) ? fim::kFarG : w;
-    }
-  }
-  {
-    // x-neighbours: halo rows -2, -1 are rows 30, 31 of tile (tx - 1, tz); rows 32, 33 are rows 0, 1 of (tx + 1, tz)
-    if (lane < 4) {
-      const unsigned m = tl.hx[lane];
-      const int ntx = lane < 2 ? tx - 1 : tx + 1;
-      if (m && ntx >= 0 && ntx < L.ntx) {
-        const int nt = ntx * L.ntz + tz;
-        atomicOr(bitmap + (size_t)nt * fim::kT + (lane < 2 ? fim::kT - 2 + lane : lane - 2), m);
-        atomicOr(active + (nt >> 5), 1u << (nt & 31));
-      }
-    }
-    // z-neighbours: halo columns -2, -1 are bits 30, 31 of tile (tx, tz - 1); columns 32, 33 are bits 0, 1 of (tx, tz + 1)
-    const unsigned lo = (((tl.hz[0] >> lane) & 1u) << 30) | (((tl.hz[1] >> lane) & 1u) << 31);
-    const unsigned hi = ((tl.hz[2] >> lane) & 1u) | (((tl.hz[3] >> lane) & 1u) << 1);
-    if (lo && tz - 1 >= 0) {
-      atomicOr(bitmap + (size_t)(tile - 1) * fim::kT + lane, lo);
-      atomicOr(active + ((tile - 1) >> 5), 1u << ((tile - 1) & 31));
-    }
-    if (hi && tz + 1 < L.ntz) {
-      atomicOr(bitmap + (size_t)(tile + 1) * fim::kT + lane, hi);
-      atomicOr(active + ((tile + 1) >> 5), 1u << ((tile + 1) & 31));
-    }
-    const unsigned left = vdirty[lane];  // walk limit reached: the tile stays active
-    if (left) {
-      atomicOr(bm + lane, left);
-      atomicOr(active + (tile >> 5), 1u << (tile & 31));
-    }
-  }
+  fim_tile_store(tl, C, L, tile, T, bitmap, active, lane, changed);
   __syncwarp();
 }
 

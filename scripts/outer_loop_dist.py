@@ -58,7 +58,7 @@ for it in range(1, args.iters + 1):
     torch.cuda.synchronize()
     if rank == 0:
         print(json.dumps(dict(
-            iter=it, n_gpus=world, workload=pb.name, sweeps=int(nnz_g[2].item()),
+            iter=it, n_gpus=world, workload=pb.name, eikonal=os.environ.get('DSURF_EIKONAL', 'exact'), sweeps=int(nnz_g[2].item()),
             sweeps_per_s=nnz_g[2].item() / (tmax[0].item() / 1e3), sweep_stage_ms=tmax[0].item(), dispersion_ms=tdisp,
             nnz_global=int(nnz_g[0].item()), nnz_global_exceeds_int32=bool(nnz_g[0].item() >= 2 ** 31), m_global=int(nnz_g[1].item()),
             nnz_this_rank=int(sysl.nnz), lsmr_itn=L["itn"], lsmr_istop=L["istop"], lsmr_iters_per_s=L["itn"] / (tmax[1].item() / 1e3),
