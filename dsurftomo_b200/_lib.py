@@ -10,7 +10,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdsurf_b200.so")
+# DSURF_B200_LIB: load another build of the same library (A/B runs of kernel variants); no fallback either way
+LIB_PATH = os.environ.get("DSURF_B200_LIB") or os.path.join(HERE, "libdsurf_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 OK = 0

@@ -15,10 +15,12 @@
 // and any relaxation order reaches it; wherever the reference's heap pops in time order the fixed point is the
 // reference's travel-time field BIT FOR BIT.  The heap deviates from time order only (a) between equal keys (heap
 // layout decides) and (b) after updtree raised a key (it only sifts up, :894-921); both are rare and local, and their
-// effect is at the last-bit level.  Measured against the oracle (scripts/research/fim_rule_study.cpp, tests/
-// test_fim_host.py, scripts/parity_stats.py): 257^2 grid -- 7 of 8 sweeps identical on every node; 1025^2 -- 0.6 % of the
-// nodes differ, by <= 4e-6 relative (p50 3e-7), no ray changes its B-spline vertex pattern.  The refined source grid
-// (early exit: its alive SET depends on the pop order) stays on the exact heap kernel (k_refine).
+// effect is at the last-bit level.  Measured (profiles/r02_fim_parity.md; scripts/fim_parity.py on the GPU, tests/
+// test_fim_host.py on the host): grids up to 257^2 -- travel-time fields, G matrices and the Vs model after an outer iteration
+// bit-identical to the exact kernel's on the Taipei example, cfg 2 and a 4-type problem; 1025^2 -- 1.5 % of the nodes differ,
+// by <= 2.2e-6 relative (p50 3.4e-7), predicted times by <= 1.3e-6, and 0.7 % of the rays change their B-spline vertex pattern
+// (a last-bit change of T is 1e-3 of a cell's traversal time there).  That is why this pipeline is opt-in.  The refined source
+// grid (early exit: its alive SET depends on the pop order) stays on the exact heap kernel (k_refine).
 //
 // RELAXATION ORDER.  Node-level dirty bits: a node is re-evaluated only after a stencil neighbour changed in a way
 // that can matter (min(old, new) < the node's time: later nodes never enter the rule).  Inside a tile the warp walks

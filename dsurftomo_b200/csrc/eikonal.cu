@@ -1217,7 +1217,10 @@ __device__ __forceinline__ void fim_process_tile(fim::TileD &tl, const fim::Tile
   for (int w = 0; w < 32; w++) {
     if (!__any_sync(kFull, vdirty[lane] != 0)) break;
     const int sx = (w & 1) ? -sx0 : sx0, sz = (w & 2) ? -sz0 : sz0;
-    float slow_pf = 0.0f;  // slowness of this lane's node on the NEXT diagonal, loaded one step ahead (off the critical path)
+    // slowness of this lane's node on the NEXT diagonal, loaded one step ahead (off the critical path).  A/B on B200
+    // (gpurun_out/r2s26_ab.log): deferring the division to the use site and a branch-free form of relax_node's marking loop
+    // were both measured and rejected (the latter is 15 % slower)
+    float slow_pf = 0.0f;
     int z_pf = -2;
     for (int dg = 0; dg < 2 * fim::kT - 1; dg++) {
       const int z = fim::diag_z(lane, dg, sx, sz);
@@ -1343,7 +1346,7 @@ k_fim_march(Geom g, SweepDesc *__restrict__ sw, int nsw, const float *__restrict
 // Pipeline selection: dsurf_set_eikonal_mode() or DSURF_EIKONAL = exact | lps | fim (DSURF_EIKONAL_LPS=1 is the older
 // spelling of lps).  Default: the exact single-kernel march with 16 lanes per sweep (k_eikonal3).
 //   lps  k_refine + k_march_lps (exact, lane per sweep, warp-specialised).  Measured on B200 at cfg 3 (profiles/
-//        r02_eikonal_lps.md): 33 s per stage against 22.6 s -- with one lane per sweep every load touches 32 distinct lines
+//        r02_eikonal_fim.md, last section): 33 s per stage against 22.6 s -- with one lane per sweep every load touches 32 distinct lines
 //        and the slowest of 32 unrelated sweeps sets the pace of each acceptance; it needs 2.4x fewer DRAM bytes and 5x
 //        fewer issue slots per accepted node, but the machine is latency-, not throughput-bound on this path.
 //   fim  k_refine + k_fim_start + k_fim_march (eik_fim.cuh): not bit-exact by construction, deviations measured.
