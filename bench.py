@@ -429,10 +429,13 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
                     roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                                   spmv_gbs=ach_spmv, spmtv_gbs=ach_spmtv,
                                   traffic=(mt["lsmr"]["dram_bytes_per_nnz_per_iter"] * sysl.nnz if mt else None),
+                                  frac_on_measured_traffic=(mt["lsmr"]["dram_bytes_per_nnz_per_iter"] * sysl.nnz * L["itn"] /
+                                                            (L["ms_total"] / 1e3) / 1e9 / peak if mt else None),
                                   traffic_source=(mt["lsmr"]["source"] if mt else None),
                                   algorithmic_bytes_per_iter=lsmr_bytes(sysl.nnz, m, n),
-                                  note="per rank; depth-blocked layout stores 1 index + 8 values per vertex: real bytes "
-                                       "are ~0.58x the algorithmic 16 B per non-zero"),
+                                  note="per rank; `frac` is on the ALGORITHMIC bytes of SURVEY.md 8(d) (16 B per non-zero) and can "
+                                       "exceed 1: the depth-blocked layout stores 1 index + 8 values per vertex, real DRAM bytes "
+                                       "are ~0.58x of that; frac_on_measured_traffic is the fraction of the copy peak really used"),
                     launches_per_iter=(6 if world == 1 else 9),
                     to_convergence=dict(iters=Lc["itn"], istop=Lc["istop"], seconds=t_conv, normr=Lc["normr"]))
         sysl.close()
