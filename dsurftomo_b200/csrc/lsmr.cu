@@ -1374,6 +1374,7 @@ struct dsurf_lsmr_sys {
   size_t xstride = 0, xbytes = 0;   // bytes of one parity slot / of the whole buffer
   DevBuf<char *> xpeers;            // device table: exchange buffers of every rank (this rank's own at [rank])
   bool xready = false;
+  std::vector<char *> xmapped;      // peers' buffers opened with cudaIpcOpenMemHandle (closed with the system)
   bool solved = false;
   // fused small-vector phases (k_fused_beta / k_fused_tail): cluster size (0 = unfused path),
   // elements of the n-vectors per CTA, dynamic shared memory of the tail kernel
@@ -1386,6 +1387,7 @@ struct dsurf_lsmr_sys {
     if (evj) cudaEventDestroy(evj);
     if (st2) cudaStreamDestroy(st2);
     if (own_stream && st) cudaStreamDestroy(st);
+    for (char *p : xmapped) cudaIpcCloseMemHandle(p);
     if (xbuf) cudaFree(xbuf);
   }
 };
@@ -1664,6 +1666,9 @@ extern "C" int dsurf_lsmr_xchg_export(dsurf_lsmr_sys *s, void *handle64) {
 }
 extern "C" int dsurf_lsmr_xchg_attach(dsurf_lsmr_sys *s, const void *handles, int rank, int nranks) {
   if (!s || !handles || !s->xbuf || rank < 0 || rank >= nranks || nranks > 64) return DSURF_ERR_BAD_ARG;
+  for (char *p : s->xmapped) cudaIpcCloseMemHandle(p);  // attached before: drop the old mappings
+  s->xmapped.clear();
+  s->xready = false;
   std::vector<char *> tab(nranks, nullptr);
   for (int r = 0; r < nranks; r++) {
     if (r == rank) {
@@ -1675,6 +1680,7 @@ extern "C" int dsurf_lsmr_xchg_attach(dsurf_lsmr_sys *s, const void *handles, in
     void *ptr = nullptr;
     DS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     tab[r] = (char *)ptr;
+    s->xmapped.push_back((char *)ptr);
   }
   if (s->xpeers.reserve(nranks)) return DSURF_ERR_CUDA;
   DS_CUDA(cudaMemcpy(s->xpeers.p, tab.data(), nranks * sizeof(char *), cudaMemcpyHostToDevice));

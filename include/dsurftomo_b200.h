@@ -277,7 +277,8 @@ int dsurf_lsmr_set_comm(dsurf_lsmr_sys *sys, void *nccl_comm, int rank, int nran
 /* peer-memory exchange of the distributed LSMR (replaces the per-iteration NCCL all-reduce by direct NVLink loads
  * from every rank's exchange buffer; the iteration becomes a CUDA graph): every rank exports the CUDA IPC handle of
  * its buffer (64 bytes), the host side all-gathers the handles (dsurftomo_b200/dist.py) and attaches them.
- * dsurf_lsmr_set_comm is still needed (the two set-up reductions of a solve use NCCL). */
+ * dsurf_lsmr_set_comm is still needed (the two set-up reductions of a solve use NCCL).  Destroy the systems only after
+ * every rank has returned from its last solve (a barrier on the host side): peers read each other's buffers. */
 int dsurf_lsmr_xchg_export(dsurf_lsmr_sys *sys, void *handle64);
 int dsurf_lsmr_xchg_attach(dsurf_lsmr_sys *sys, const void *handles /* nranks x 64 bytes */, int rank, int nranks);
 int dsurf_nccl_unique_id(void *id128);
