@@ -92,3 +92,30 @@ def test_fim_batched_and_chunked_equals_unbatched(fim_mode, monkeypatch):
     assert np.abs(got["dsurf"] / ref["dsurf"] - 1).max() <= 1e-6
     assert got["nar"] == ref["nar"] and np.array_equal(got["col"], ref["col"])
     assert np.abs(got["rw"] - ref["rw"]).max() <= 1e-5 * np.abs(ref["rw"]).max()
+
+
+def test_fim_full_size_field_within_north_star_tolerance(fim_mode):
+    """1025 x 1025 propagation grid (BASELINE configs[2]): every node reached, travel times within 1e-5 relative of the
+    oracle's heap march (measured <= 2.2e-6), only a few per cent of the nodes differ at all, |grad T| bounded"""
+    pb = inputs.synthetic_problem(131, 1, 8, ("Rc",), nrecv=16, name="fim_full_size")
+    pv4, sen12 = inputs.synthetic_dispersion(pb)
+    plan = api.Plan(pb)
+    plan.set_dispersion(0, pv4[0], *sen12[0:3])
+    plan.finalize_dispersion()
+    tot = dif = 0
+    for g in (1, 6):
+        got = plan.debug_sweep(g, 1, want_fdm=False)
+        ref = O.fmm_sweep(pb.nx, pb.ny, pb.goxd, pb.gozd, pb.dvxd, pb.dvzd, pv4[0][0], pb.scxf[0, g], pb.sczf[0, g])
+        assert ref["err"] == 0 and got["ttn"].shape == (1025, 1025)
+        assert np.array_equal(_bits(got["veln"]), _bits(ref["veln"]))
+        t = got["ttn"]
+        assert np.isfinite(t).all() and t.min() >= 0.0 and t.max() < 1e30
+        pos = ref["ttn"] > 0
+        assert np.abs(t[pos] / ref["ttn"][pos] - 1).max() <= 1e-5
+        d = _bits(t) != _bits(ref["ttn"])
+        tot += d.size
+        dif += int(d.sum())
+        h = 6371.0 * np.deg2rad(pb.dvxd) / 8
+        assert max(np.abs(np.diff(t, axis=0)).max(), np.abs(np.diff(t, axis=1)).max()) <= 1.5 * h / got["veln"].min()
+    assert dif <= 0.1 * tot, (dif, tot)
+    plan.close()
