@@ -40,8 +40,6 @@ constexpr int kPitch = kT + 2 * kHZ;   // 40 words per tile row: lane l on an an
 constexpr uint32_t kFarG = 0xFFFFFFFFu;  // global array: far node / outside the grid
 constexpr uint32_t kInf = 0x7f800000u;   // tile copy: far (+inf)
 constexpr uint32_t kInit = 0x80000000u;  // tile copy: flag "alive before the pass" (times are never negative)
-constexpr uint32_t kOutside = 0xFF800000u;  // tile copy (DSURF_FIM_NOBOUNDS): node outside the grid = flagged +inf: never a
-                                            // user to mark, never recomputed, never alive in a second-order leg
 constexpr int kTileWords = kRows * kPitch;
 
 // global layout of one sweep's time field: node (ix, iz) 0-based at (ix + kHX) * pitch + iz + kHZ; rows
@@ -262,12 +260,7 @@ LPS_HD bool relax_node(TL &tl, const TileCtx &C, int x, int z, float slown) {
     const int dz = q == 0 ? -2 : q == 1 ? -1 : q == 2 ? 1 : 2;
     const int uz = z + dz, ugz = gz + dz;
     const uint32_t uw = c[dz];
-#if defined(DSURF_FIM_NOBOUNDS)
-    (void)ugz;
-    if ((int)uw < 0 || mn >= as_f(uw)) continue;  // also skips nodes outside the grid (kOutside)
-#else
     if (ugz < 0 || ugz >= C.nnz || (int)uw < 0 || mn >= as_f(uw)) continue;
-#endif
     if (uz < 0)
       DSURF_FIM_OR(&tl.hz[uz + 2], 1u << x);
     else if (uz >= kT)
@@ -283,12 +276,7 @@ LPS_HD bool relax_node(TL &tl, const TileCtx &C, int x, int z, float slown) {
     const int dx = q == 0 ? -2 : q == 1 ? -1 : q == 2 ? 1 : 2;
     const int ux = x + dx, ugx = gx + dx;
     const uint32_t uw = c[dx * kPitch];
-#if defined(DSURF_FIM_NOBOUNDS)
-    (void)ugx;
-    if ((int)uw < 0 || mn >= as_f(uw)) continue;
-#else
     if (ugx < 0 || ugx >= C.nnx || (int)uw < 0 || mn >= as_f(uw)) continue;
-#endif
     if (ux < 0)
       DSURF_FIM_OR(&tl.hx[ux + 2], 1u << z);
     else if (ux >= kT)

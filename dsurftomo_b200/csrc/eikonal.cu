@@ -1119,10 +1119,6 @@ __device__ __forceinline__ void fim_tile_load(fim::TileD &tl, const fim::TileCtx
                        C.gz0 - fim::kHZ < C.bz0 + C.bh && C.gz0 + fim::kT + fim::kHZ > C.bz0;
   const uint4 *src = reinterpret_cast<const uint4 *>(T + (size_t)C.gx0 * L.pitch + C.gz0);  // row gx0 - kHX, column gz0 - kHZ
   constexpr int kVecRow = fim::kPitch / 4;
-#if defined(DSURF_FIM_NOBOUNDS)
-  const bool edge = C.gx0 - fim::kHX < 0 || C.gx0 + fim::kT + fim::kHX > C.nnx || C.gz0 - fim::kHZ < 0 ||
-                    C.gz0 + fim::kT + fim::kHZ > C.nnz;
-#endif
   if (TMA) {
     // the 36 rows (160 bytes each, 16-byte aligned) go through the TMA engine; one mbarrier per tile buffer counts the bytes
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the tile buffer
@@ -1140,16 +1136,6 @@ __device__ __forceinline__ void fim_tile_load(fim::TileD &tl, const fim::TileCtx
     v.y = (int)v.y < 0 ? fim::kInf : v.y;
     v.z = (int)v.z < 0 ? fim::kInf : v.z;
     v.w = (int)v.w < 0 ? fim::kInf : v.w;
-#if defined(DSURF_FIM_NOBOUNDS)
-    if (edge) {  // tiles on the rim of the grid: flag the words outside it
-      const int gx = C.gx0 + r - fim::kHX, gz = C.gz0 + 4 * c4 - fim::kHZ;
-      const bool xo = gx < 0 || gx >= C.nnx;
-      unsigned *e = &v.x;
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (xo || gz + k < 0 || gz + k >= C.nnz) e[k] = fim::kOutside;
-    }
-#endif
     if (touches) {
       const int bx = C.gx0 + r - fim::kHX - C.bx0, bz = C.gz0 + 4 * c4 - fim::kHZ - C.bz0;
       if (bx >= 0 && bx < C.bw) {
@@ -1232,8 +1218,9 @@ __device__ __forceinline__ void fim_process_tile(fim::TileD &tl, const fim::Tile
     if (!__any_sync(kFull, vdirty[lane] != 0)) break;
     const int sx = (w & 1) ? -sx0 : sx0, sz = (w & 2) ? -sz0 : sz0;
     // slowness of this lane's node on the NEXT diagonal, loaded one step ahead (off the critical path).  A/B on B200
-    // (gpurun_out/r2s26_ab.log): deferring the division to the use site and a branch-free form of relax_node's marking loop
-    // were both measured and rejected (the latter is 15 % slower)
+    // (profiles/r02_fim_source_variants_ab.log, r02_fim_marking_variants_ab.log): deferring the division to the use site, a
+    // branch-free marking loop in relax_node, marking without bounds tests (out-of-grid words flagged at load), re-using the
+    // stencil words in the marking loop and 7 resident CTAs per SM were all measured and rejected (same COO digest, 4-25 % slower)
     float slow_pf = 0.0f;
     int z_pf = -2;
     for (int dg = 0; dg < 2 * fim::kT - 1; dg++) {
@@ -1448,7 +1435,6 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
     DS_CUDA(cudaFuncSetAttribute(k_fim_march<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DS_CUDA(cudaFuncSetAttribute(k_fim_march<6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DS_CUDA(cudaFuncSetAttribute(k_fim_march<5, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    DS_CUDA(cudaFuncSetAttribute(k_fim_march<7, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   if (mode == kEikExact16) {
@@ -1475,7 +1461,6 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
       DS_CUDA(cudaFuncSetAttribute(k_fim_march<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
       DS_CUDA(cudaFuncSetAttribute(k_fim_march<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
       DS_CUDA(cudaFuncSetAttribute(k_fim_march<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-      DS_CUDA(cudaFuncSetAttribute(k_fim_march<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
       fsm_set = fsm;
     }
     // resident CTAs per SM the kernel is compiled for (4 sweeps each): 6 = 80 registers per thread (default), 4 = 128, 8 = 64
@@ -1492,8 +1477,6 @@ int launch_eikonal(cudaStream_t st, const Geom &g, const SweepDesc *d_sw, int ns
       k_fim_march<8, false><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
     else if (minb == 5)
       k_fim_march<5, true><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
-    else if (minb == 7)
-      k_fim_march<7, true><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
     else if (tma)
       k_fim_march<6, true><<<fgrid, fnt, fsm, st>>>(g, sw, nsw, d_veln_all, d_risti, bv, L);
     else

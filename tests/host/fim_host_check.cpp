@@ -53,9 +53,6 @@ struct HostSweep {
         const int gx = C.gx0 + r - kHX, gz = C.gz0 + c - kHZ;
         uint32_t w = T[(size_t)(gx + kHX) * L.pitch + (gz + kHZ)];
         if ((int)w < 0) w = kInf;
-#if defined(DSURF_FIM_NOBOUNDS)
-        if (gx < 0 || gx >= C.nnx || gz < 0 || gz >= C.nnz) w = kOutside;
-#endif
         const int bx = gx - C.bx0, bz = gz - C.bz0;
         if (bx >= 0 && bx < C.bw && bz >= 0 && bz < C.bh && C.box[2 * (bx * C.bh + bz) + 1] == 0) w |= kInit;
         tl.t[r * kPitch + c] = w;
