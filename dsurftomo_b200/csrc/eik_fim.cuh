@@ -1,5 +1,5 @@
 // K3-FIM -- the coarse-grid pass of travel (src/CalSurfG.f90:386-486, fouds2 :587-759) as a BLOCK-LEVEL
-// FAST ITERATIVE sweep: no heap, no pop order; 32 x 32 node tiles are relaxed in shared memory by one warp each
+// FAST ITERATIVE sweep: no heap, no pop order; one warp per sweep relaxes 32 x 32 node tiles in shared memory
 // and tiles re-activate their neighbours until nothing changes.  Shared by the device kernel (eikonal.cu,
 // k_fim_march) and the host replay (tests/host/fim_host_check.cpp), which runs the same per-node code against the
 // oracle's heap march.
@@ -10,10 +10,12 @@
 //     v = the node's injected time if it starts as a close node (travel(urg=2) seeds, :341-347), else +inf
 //     for its neighbours J that are popped during this pass, in increasing T(J):
 //         if T(J) < v:   v = fouds2(node | alive = nodes alive before the pass + nodes with T <= T(J))   else stop
-// rule() below evaluates exactly this with the reference's fp32 operation order (lps::fouds2_words, the routine the
-// exact kernels use).  The rule is causal -- v depends only on nodes with smaller times -- so it has ONE fixed point
-// and any relaxation order reaches it; wherever the reference's heap pops in time order the fixed point is the
-// reference's travel-time field BIT FOR BIT.  The heap deviates from time order only (a) between equal keys (heap
+// rule_generic() below evaluates exactly this with the reference's fp32 operation order (lps::fouds2_words, the routine
+// the exact kernels use); rule() is the same function in straight-line code for the common case.  The rule is causal -- v
+// depends only on nodes with smaller times -- so wherever trial values only decrease it has ONE fixed point and any
+// relaxation order reaches it (in the rare non-monotone spots the order can matter in the last bits: 6 nodes of 2.1e6
+// between two tile orders on the host replay; the device order is fixed, one warp per sweep).  Wherever the reference's
+// heap pops in time order the fixed point is the reference's travel-time field BIT FOR BIT.  The heap deviates from time order only (a) between equal keys (heap
 // layout decides) and (b) after updtree raised a key (it only sifts up, :894-921); both are rare and local, and their
 // effect is at the last-bit level.  Measured (profiles/r02_fim_parity.md; scripts/fim_parity.py on the GPU, tests/
 // test_fim_host.py on the host): grids up to 257^2 -- travel-time fields, G matrices and the Vs model after an outer iteration
