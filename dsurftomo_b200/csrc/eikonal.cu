@@ -1121,7 +1121,9 @@ __device__ __forceinline__ void fim_tile_load(fim::TileD &tl, const fim::TileCtx
   constexpr int kVecRow = fim::kPitch / 4;
   if (TMA) {
     // the 36 rows (160 bytes each, 16-byte aligned) go through the TMA engine; one mbarrier per tile buffer counts the bytes
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the tile buffer
+    // generic-proxy accesses made so far -- the tile buffer in shared memory AND the previous tile's interior stored to the
+    // field in global memory, which this load's halo may overlap -- before the async-proxy reads below
+    asm volatile("fence.proxy.async;" ::: "memory");
     if (lane == 0) mbar_expect_tx(bar, fim::kRows * fim::kPitch * 4);
     __syncwarp();
     for (int r = lane; r < fim::kRows; r += 32)
