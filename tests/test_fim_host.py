@@ -31,6 +31,10 @@ def test_fim_host_replay_matches_heap_march(exe, nx, nsrc, rough):
     assert r.returncode == 0 and "FIM HOST CHECK OK" in r.stdout, r.stdout[-3000:]
     m = re.search(r"mismatch_frac=(\S+) max_rel=(\S+) unreached=(\d+) rays=(\d+) rays_pattern_diff=(\d+)", r.stdout)
     assert m and int(m.group(3)) == 0 and int(m.group(5)) == 0 and float(m.group(2)) <= 1e-5
+    # the exact start-up: every node it accepted carries the reference's final time bit for bit; the straight-line rule
+    # equals the plain one on every evaluation
+    assert re.search(r"differing from the reference's final times: 0\b", r.stdout)
+    assert re.search(r"cached_vs_plain_mismatch=0\b", r.stdout)
 
 
 def test_fim_uniform_field_is_bit_identical(exe):
