@@ -495,8 +495,8 @@ def run_b200(args, pb, pv4, sen12, blocks, tblocks):
                          coo=dict(nar=int(M2["nar_total"]), digest=f"{M2['digest'][0]:016x}"),
                          parity=("travel times bit-identical to the reference" if om == "exact" else
                                  "iterates the reference's own update rule: <= 2.2e-6 relative on travel times at 1025^2 (1.5 % of "
-                                 "the nodes, last bits), 0.7 % of the rays change their B-spline vertex pattern at 1025^2, none "
-                                 "at <= 257^2; profiles/r02_fim_parity.md"))
+                                 "the nodes, last bits); 0.7 % of the rays differ in their G entries at 1025^2 (0.1 % through another "
+                                 "B-spline cell, the rest through the ftol thresholds), none at <= 257^2; profiles/r02_fim_parity.md"))
     if rank == 0:
         cfg = make_config(pb, world, args.step_mode)
         out = dict(metric=METRIC, value=value, unit="sweeps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,

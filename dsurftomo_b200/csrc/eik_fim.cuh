@@ -20,8 +20,8 @@
 // effect is at the last-bit level.  Measured (profiles/r02_fim_parity.md; scripts/fim_parity.py on the GPU, tests/
 // test_fim_host.py on the host): grids up to 257^2 -- travel-time fields, G matrices and the Vs model after an outer iteration
 // bit-identical to the exact kernel's on the Taipei example, cfg 2 and a 4-type problem; 1025^2 -- 1.5 % of the nodes differ,
-// by <= 2.2e-6 relative (p50 3.4e-7), predicted times by <= 1.3e-6, and 0.7 % of the rays change their B-spline vertex pattern
-// (a last-bit change of T is 1e-3 of a cell's traversal time there).  That is why this pipeline is opt-in.  The refined source
+// by <= 2.2e-6 relative (p50 3.4e-7), predicted times by <= 1.3e-6, and 0.7 % of the rays differ in their G entries (0.1 % because
+// a ray point falls into another B-spline cell: a last-bit change of T is 1e-3 of a cell's traversal time there).  That is why this pipeline is opt-in.  The refined source
 // grid (early exit: its alive SET depends on the pop order) stays on the exact heap kernel (k_refine).
 //
 // RELAXATION ORDER.  Node-level dirty bits: a node is re-evaluated only after a stencil neighbour changed in a way
